@@ -1,0 +1,680 @@
+"""CUDA code generator: problem structure -> one fused FP64 translation unit.
+
+This replaces the reference's sympy -> NumPy code generation
+(``sym2num`` / ``symoptim.compile_class``; call sites
+/root/reference/attas_sp_ml.py:85-86, /root/reference/mc_blackbox_cfem.py:86-95)
+with a generator of sm_100a CUDA.  Input is ``optim.Structure`` (N-independent);
+output is the source of ONE shared library that exports the C ABI of
+``include/cfem.h``.  The generated text contains only what depends on the
+model: the structure tables and the straight-line expression code of every
+structural nonzero.  The machinery around it (staging, per-warp output
+transposition, reductions, the whole host side) is the hand-written code in
+``csrc/cfem_device.cuh`` and ``csrc/cfem_host.inl``.
+
+Kernels per library
+  cfem_sample_kernel_m<mask>  one thread per sample, one CTA per tile of
+      CFEM_TILE samples and (blockIdx.y) per problem of a batch; evaluates every
+      per-sample function selected by ``mask`` (objective partial sums,
+      gradient block, constraint values, Jacobian blocks, Hessian blocks) from
+      one staging of the tile's inputs;
+  cfem_param_kernel           one thread per entry of the parameter-only
+      functions (values, Jacobian, Hessian);
+  cfem_finalize_kernel        fixed-order reduction over tiles + the
+      sample-independent objective terms (times the row count);
+  cfem_apply_reduced_kernel   writes an externally all-reduced objective /
+      parameter-gradient vector back (time-sharded multi-GPU runs).
+"""
+
+import json
+import os
+
+from . import symoptim
+
+F, GRAD, G, JAC, HESS = 1, 2, 4, 8, 16
+ALL = 31
+
+#: kernel variants that are instantiated (a request is served by the smallest
+#: superset): single callbacks, IPOPT's usual groupings and the full set.
+DEFAULT_MASKS = (F, F | GRAD, G, JAC, HESS, F | G, F | GRAD | G | JAC, ALL)
+
+
+def _pad_odd(c):
+    return c | 1
+
+
+class _Item:
+    """One output block a sample kernel produces for one function."""
+
+    def __init__(self, c, codes, dest, mult=None):
+        self.c = c              # doubles per sample
+        self.codes = codes      # C expression per element
+        self.dest = dest        # C expression: pointer to row 0 of the block
+        self.mult = mult        # optional C expressions multiplied in
+
+
+class Generator:
+    def __init__(self, structure, tile=None, pass_budget=None, masks=None):
+        self.st = structure
+        self.masks = tuple(masks or DEFAULT_MASKS)
+        self.funs = structure.funs
+        self.sample_funs = [i for i, f in enumerate(self.funs)
+                            if f['per_sample']]
+        self.param_funs = [i for i, f in enumerate(self.funs)
+                           if not f['per_sample']]
+        inputs = sum(v['core'] for v in structure.vars if v['per_sample']) \
+            + sum(d['core'] for d in structure.data) \
+            + sum(self.funs[i]['out_core'] for i in self.sample_funs
+                  if not self.funs[i]['is_objective'])
+        if tile is None:
+            tile = int(os.environ.get('CFEM_TILE', 0)) or \
+                (256 if inputs <= 16 else 128)
+        if pass_budget is None:
+            pass_budget = int(os.environ.get('CFEM_PASS_BUDGET', 0)) or 24
+        assert tile % 32 == 0 and 32 <= tile <= 1024
+        self.tile = tile
+        self.pass_budget = pass_budget
+        self._reduce_slots()
+
+    # ------------------------------------------------------------------
+    # classification helpers
+    # ------------------------------------------------------------------
+    def _is_sample_dep(self, fun, deps):
+        return any(fun['args'][a][0] in ('var', 'data') for a, _ in deps)
+
+    def _reduce_slots(self):
+        """Slot 0 is the objective; then one slot per structural parameter
+        entry of the objective gradient.  ``dyn`` slots have per-sample terms
+        and therefore per-tile partial sums."""
+        self.slots = [{'var': -1, 'flat': 0, 'dyn': True}]
+        self.slot_of = {}
+        for fi, f in enumerate(self.funs):
+            if not f['is_objective']:
+                continue
+            spec = f['spec']
+            for wrt in spec.wrt:
+                ref = f['args'][wrt]
+                if ref[0] != 'param' or wrt not in spec.jac:
+                    continue
+                for e in spec.jac[wrt]:
+                    key = (ref[1], e.index[0])
+                    dyn = f['per_sample'] and any(
+                        self._is_sample_dep(f, d) for _, d in e.terms)
+                    if key not in self.slot_of:
+                        self.slot_of[key] = len(self.slots)
+                        self.slots.append({'var': key[0], 'flat': key[1],
+                                           'dyn': False})
+                    if dyn:
+                        self.slots[self.slot_of[key]]['dyn'] = True
+        self.dyn_slots = [i for i, s in enumerate(self.slots) if s['dyn']]
+        self.dyn_index = {s: i for i, s in enumerate(self.dyn_slots)}
+
+    # ------------------------------------------------------------------
+    # identifiers
+    # ------------------------------------------------------------------
+    def _define_args(self, fun, deps, where, layout=None):
+        """#define / const lines binding v_<arg>_<flat> for ``deps``.
+
+        where: 'sample' (tile in shared memory), 'global' (dvec in HBM).
+        Returns (lines, undef_lines).
+        """
+        lines, undefs = [], []
+        for a, flat in sorted(set(deps)):
+            ident = symoptim.c_ident(a, flat)
+            ref = fun['args'][a]
+            if ref[0] == 'param':
+                if where == 'sample':
+                    off = layout['param_off'][ref[1]] + flat
+                    lines.append(f'#define {ident} sp[{off}]')
+                else:
+                    lines.append(f'#define {ident} dvec[a.var_off[{ref[1]}] '
+                                 f'+ {flat}]')
+                undefs.append(f'#undef {ident}')
+            elif ref[0] == 'scalar':
+                lines.append(f'#define {ident} a.scalars[{ref[1]}]')
+                undefs.append(f'#undef {ident}')
+            else:
+                assert where == 'sample'
+                key = (ref[0], ref[1])
+                st = layout['stor'][key]
+                lines.append(
+                    f'const double {ident} = {st["name"]}'
+                    f'[(tid + {ref[2]}) * {st["pad"]} + {flat}];')
+        return lines, undefs
+
+    # ------------------------------------------------------------------
+    # per-mask plan of a sample kernel
+    # ------------------------------------------------------------------
+    def _plan(self, mask):
+        """Items, reductions and needed symbols per per-sample function."""
+        plan = []
+        st = self.st
+        jac_of = {}
+        for bi, b in enumerate(st.jac_blocks):
+            jac_of.setdefault(b['fun'], []).append((bi, b))
+        hess_of = {}
+        for bi, b in enumerate(st.hess_blocks):
+            hess_of.setdefault(b['fun'], []).append((bi, b))
+        for fi in self.sample_funs:
+            f = self.funs[fi]
+            spec = f['spec']
+            items, reds, deps = [], [], []
+            lam_needed = False
+            if f['is_objective']:
+                if mask & (F | GRAD):
+                    for e in spec.values:
+                        for code, d in e.terms:
+                            if self._is_sample_dep(f, d):
+                                reds.append((0, code))
+                                deps += d
+                    for wrt in spec.wrt:
+                        ref = f['args'][wrt]
+                        if ref[0] != 'param':
+                            continue
+                        for e in spec.jac.get(wrt, []):
+                            slot = self.slot_of[(ref[1], e.index[0])]
+                            for code, d in e.terms:
+                                if self._is_sample_dep(f, d):
+                                    reds.append((slot, code))
+                                    deps += d
+                if mask & GRAD:
+                    for wrt in spec.wrt:
+                        ref = f['args'][wrt]
+                        if ref[0] != 'var' or wrt not in spec.jac:
+                            continue
+                        core = spec.core_size(wrt)
+                        codes = ['0.0'] * core
+                        for e in spec.jac[wrt]:
+                            assert e.index[1] == 0
+                            codes[e.index[0]] = e.code
+                            deps += e.deps
+                        dest = (f'a.grad + b * a.ndec + a.var_off[{ref[1]}] '
+                                f'+ {ref[2] * core}')
+                        items.append(_Item(core, codes, dest))
+            else:
+                ci = f['cons_index']
+                if mask & G:
+                    codes = [e.code for e in spec.values]
+                    for e in spec.values:
+                        deps += e.deps
+                    items.append(_Item(
+                        f['out_core'], codes,
+                        f'a.g + b * a.ncons + a.cons_off[{ci}]'))
+                if mask & JAC:
+                    for bi, blk in jac_of.get(fi, []):
+                        for e in blk['entries']:
+                            deps += e.deps
+                        items.append(_Item(
+                            blk['c'], [e.code for e in blk['entries']],
+                            f'a.jac + b * a.nnz_jac + a.jac_off[{bi}]'))
+            if mask & HESS:
+                for bi, blk in hess_of.get(fi, []):
+                    if f['is_objective']:
+                        mult = ['a.obj_factor'] * blk['c']
+                    else:
+                        mult = [f'lam_{fi}_{e.index[2]}'
+                                for e in blk['entries']]
+                        lam_needed = True
+                    for e in blk['entries']:
+                        deps += e.deps
+                    items.append(_Item(
+                        blk['c'], [e.code for e in blk['entries']],
+                        f'a.hess + b * a.nnz_hess + a.hess_off[{bi}]', mult))
+            if items or reds:
+                plan.append({'fi': fi, 'items': items, 'reds': reds,
+                             'deps': sorted(set(deps)),
+                             'lam': lam_needed})
+        return plan
+
+    def _smem_layout(self, plan):
+        """Shared-memory carve-up (in doubles) of one sample kernel."""
+        off = 0
+        param_off = {}
+        stor = {}
+        for p in plan:
+            f = self.funs[p['fi']]
+            for a, _ in p['deps']:
+                ref = f['args'][a]
+                if ref[0] == 'param' and ref[1] not in param_off:
+                    param_off[ref[1]] = None
+                elif ref[0] in ('var', 'data'):
+                    key = (ref[0], ref[1])
+                    s = stor.setdefault(key, {'shift': 0})
+                    s['shift'] = max(s['shift'], ref[2])
+            if p['lam']:
+                stor[('lam', p['fi'])] = {'shift': 0}
+        for v in sorted(param_off):
+            param_off[v] = off
+            off += self.st.vars[v]['core']
+        for key in sorted(stor):
+            s = stor[key]
+            if key[0] == 'var':
+                core = self.st.vars[key[1]]['core']
+            elif key[0] == 'data':
+                core = self.st.data[key[1]]['core']
+            else:
+                core = self.funs[key[1]]['out_core']
+            s['core'] = core
+            s['pad'] = core if core == 1 else _pad_odd(core)
+            s['nrows'] = self.tile + s['shift']
+            s['name'] = f's_{key[0]}{key[1]}'
+            off += off & 1      # keep 16-byte alignment of every region
+            s['off'] = off
+            off += s['nrows'] * s['pad']
+        # output passes: group the items of every function under the budget
+        wbuf = 0
+        for p in plan:
+            passes, cur, used = [], [], 0
+            for it in p['items']:
+                need = 0 if it.c == 1 else _pad_odd(it.c)
+                if cur and used + need > self.pass_budget:
+                    passes.append(cur)
+                    cur, used = [], 0
+                cur.append(it)
+                used += need
+            if cur:
+                passes.append(cur)
+            p['passes'] = passes
+            for ps in passes:
+                wbuf = max(wbuf, sum(0 if it.c == 1 else 32 * _pad_odd(it.c)
+                                     for it in ps))
+        warps = self.tile // 32
+        off += off & 1
+        red_off = off
+        off += warps * max(1, len(self.dyn_slots))
+        off += off & 1
+        wbuf_off = off
+        off += warps * wbuf
+        return {'param_off': param_off, 'stor': stor, 'red_off': red_off,
+                'wbuf_off': wbuf_off, 'wbuf': wbuf, 'total': off}
+
+    # ------------------------------------------------------------------
+    # emitters
+    # ------------------------------------------------------------------
+    def _emit_sample_kernel(self, mask):
+        plan = self._plan(mask)
+        lay = self._smem_layout(plan)
+        T = self.tile
+        nred = len(self.dyn_slots)
+        w = []
+        w.append(f'// mask {mask}: ' + ' '.join(
+            n for n, bit in (('F', F), ('GRAD', GRAD), ('G', G), ('JAC', JAC),
+                             ('HESS', HESS)) if mask & bit))
+        w.append(f'constexpr size_t kSmemBytes_m{mask} = {lay["total"] * 8};')
+        w.append(f'__global__ void __launch_bounds__({T})')
+        w.append(f'cfem_sample_kernel_m{mask}(const cfem::KArgs a)')
+        w.append('{')
+        w.append('    extern __shared__ __align__(16) double smem[];')
+        w.append('    const int tid = threadIdx.x, lane = tid & 31, '
+                 'warp = tid >> 5;')
+        w.append('    const long long b = blockIdx.y;')
+        w.append(f'    const long long k0 = (long long)blockIdx.x * {T};')
+        w.append('    const long long kw = k0 + warp * 32;')
+        w.append('    const long long k = k0 + tid;')
+        w.append('    const double* __restrict__ dvec = a.dvec + b * a.ndec;')
+        w.append('    (void)lane; (void)kw; (void)k; (void)dvec;')
+        w.append('    double* const sp = smem;')
+        w.append(f'    double* const wb = smem + {lay["wbuf_off"]} + warp * '
+                 f'{lay["wbuf"]};')
+        w.append('    (void)sp; (void)wb;')
+        # staging
+        for v, off in sorted(lay['param_off'].items()):
+            w.append(f'    cfem::stage_contig(sp + {off}, dvec + '
+                     f'a.var_off[{v}], {self.st.vars[v]["core"]}, tid);')
+        for key in sorted(lay['stor']):
+            s = lay['stor'][key]
+            w.append(f'    double* const {s["name"]} = smem + {s["off"]};')
+            if key[0] == 'var':
+                src = f'dvec + a.var_off[{key[1]}]'
+                rows = f'a.var_rows[{key[1]}]'
+            elif key[0] == 'data':
+                src = (f'a.data[{key[1]}] + b * a.data_rows[{key[1]}] * '
+                       f'{s["core"]}')
+                rows = f'a.data_rows[{key[1]}]'
+            else:
+                ci = self.funs[key[1]]['cons_index']
+                src = f'a.lam + b * a.ncons + a.cons_off[{ci}]'
+                rows = f'a.fun_rows[{key[1]}]'
+            w.append(f'    cfem::stage_rows<{s["core"]}, {s["pad"]}, '
+                     f'{s["nrows"]}>({s["name"]}, {src}, {rows}, k0, tid);')
+        w.append('    __syncthreads();')
+        if nred and (mask & (F | GRAD)):
+            w.append(f'    double red[{nred}];')
+            w.append(f'    for (int r = 0; r < {nred}; ++r) red[r] = 0.0;')
+        for p in plan:
+            fi = p['fi']
+            f = self.funs[fi]
+            w.append(f'    // ---- {f["name"]}')
+            w.append('    {')
+            w.append(f'        const long long M = a.fun_rows[{fi}];')
+            w.append('        const long long left = M - kw;')
+            w.append('        const int nvalid = left >= 32 ? 32 : '
+                     '(left > 0 ? (int)left : 0);')
+            w.append('        const bool act = k < M;')
+            w.append('        (void)act;')
+            w.append('        if (nvalid > 0) {')
+            defs, undefs = self._define_args(f, p['deps'], 'sample', lay)
+            w += ['        ' + d if d.startswith('#') else '            ' + d
+                  for d in defs]
+            if p['lam']:
+                s = lay['stor'][('lam', fi)]
+                for o in range(f['out_core']):
+                    w.append(f'            const double lam_{fi}_{o} = '
+                             f'{s["name"]}[tid * {s["pad"]} + {o}];')
+            for slot, code in p['reds']:
+                w.append(f'            red[{self.dyn_index[slot]}] += '
+                         f'act ? ({code}) : 0.0;')
+            for ps in p['passes']:
+                wboff = 0
+                staged = []
+                for n, it in enumerate(ps):
+                    w.append('            {')
+                    if it.c == 1:
+                        val = it.codes[0]
+                        if it.mult:
+                            val = f'({it.mult[0]}) * ({val})'
+                        w.append(f'                cfem::lane_store(({it.dest})'
+                                 f' + kw, lane, nvalid, {val});')
+                    else:
+                        w.append(f'                double o[{it.c}];')
+                        for j, code in enumerate(it.codes):
+                            if it.mult:
+                                code = f'({it.mult[j]}) * ({code})'
+                            w.append(f'                o[{j}] = {code};')
+                        w.append(f'                cfem::warp_put<{it.c}>'
+                                 f'(wb + {wboff}, lane, o);')
+                        staged.append((it, wboff))
+                        wboff += 32 * _pad_odd(it.c)
+                    w.append('            }')
+                if staged:
+                    w.append('            __syncwarp();')
+                    for it, wboff in staged:
+                        w.append(f'            cfem::warp_flush<{it.c}>(wb + '
+                                 f'{wboff}, lane, ({it.dest}) + kw * {it.c}, '
+                                 'nvalid);')
+                    w.append('            __syncwarp();')
+            w += ['        ' + u for u in undefs]
+            w.append('        }')
+            w.append('    }')
+        if mask & (F | GRAD):
+            w.append(f'    cfem::block_reduce_store<{max(nred, 1)}>(red, smem + '
+                     f'{lay["red_off"]}, a.partials + ((b * a.ntiles + '
+                     f'blockIdx.x) * {max(nred, 1)}), tid);')
+        w.append('}')
+        return '\n'.join(w), lay['total'] * 8
+
+    def _param_entries(self):
+        """(kind bit, dest expr, value code, fun) for every entry of the
+        parameter-only functions; grouped G, JAC, HESS."""
+        st = self.st
+        ents = {G: [], JAC: [], HESS: []}
+        for fi in self.param_funs:
+            f = self.funs[fi]
+            spec = f['spec']
+            if f['is_objective']:
+                continue
+            ci = f['cons_index']
+            for e in spec.values:
+                ents[G].append((f, e.deps, f'a.g[b * a.ncons + '
+                                f'a.cons_off[{ci}] + {e.index[0]}]', e.code))
+        for bi, blk in enumerate(st.jac_blocks):
+            f = self.funs[blk['fun']]
+            if f['per_sample']:
+                continue
+            for j, e in enumerate(blk['entries']):
+                ents[JAC].append((f, e.deps, f'a.jac[b * a.nnz_jac + '
+                                  f'a.jac_off[{bi}] + {j}]', e.code))
+        for bi, blk in enumerate(st.hess_blocks):
+            f = self.funs[blk['fun']]
+            if f['per_sample']:
+                continue
+            for j, e in enumerate(blk['entries']):
+                if f['is_objective']:
+                    mult = 'a.obj_factor'
+                else:
+                    mult = (f'lam[a.cons_off[{f["cons_index"]}] + '
+                            f'{e.index[2]}]')
+                ents[HESS].append((f, e.deps, f'a.hess[b * a.nnz_hess + '
+                                   f'a.hess_off[{bi}] + {j}]',
+                                   f'({mult}) * ({e.code})'))
+        return ents
+
+    def _emit_param_kernel(self):
+        ents = self._param_entries()
+        order = ents[G] + ents[JAC] + ents[HESS]
+        n_g, n_j = len(ents[G]), len(ents[JAC])
+        self.n_param_entries = len(order)
+        w = []
+        w.append('__global__ void __launch_bounds__(64)')
+        w.append('cfem_param_kernel(const cfem::KArgs a, const unsigned mask)')
+        w.append('{')
+        w.append('    const int e = blockIdx.x * 64 + threadIdx.x;')
+        w.append('    const long long b = blockIdx.y;')
+        w.append('    const double* __restrict__ dvec = a.dvec + b * a.ndec;')
+        w.append('    const double* __restrict__ lam = a.lam + b * a.ncons;')
+        w.append('    (void)dvec; (void)lam;')
+        w.append(f'    if (e >= {len(order)}) return;')
+        w.append(f'    if (e < {n_g}) {{ if (!(mask & {G}u)) return; }}')
+        w.append(f'    else if (e < {n_g + n_j}) '
+                 f'{{ if (!(mask & {JAC}u)) return; }}')
+        w.append(f'    else {{ if (!(mask & {HESS}u)) return; }}')
+        w.append('    switch (e) {')
+        for i, (f, deps, dest, code) in enumerate(order):
+            w.append(f'    case {i}: {{')
+            defs, undefs = self._define_args(f, deps, 'global')
+            w += defs
+            w.append(f'        {dest} = {code};')
+            w += undefs
+            w.append('        break; }')
+        w.append('    default: break;')
+        w.append('    }')
+        w.append('}')
+        return '\n'.join(w)
+
+    def _emit_finalize(self):
+        R = len(self.slots)
+        nd = max(1, len(self.dyn_slots))
+        w = []
+        w.append('__global__ void __launch_bounds__(256)')
+        w.append('cfem_finalize_kernel(const cfem::KArgs a, const unsigned mask)')
+        w.append('{')
+        w.append('    __shared__ double scratch[8];')
+        w.append('    const int tid = threadIdx.x;')
+        w.append('    const long long b = blockIdx.x;')
+        w.append('    const double* __restrict__ dvec = a.dvec + b * a.ndec;')
+        w.append(f'    const double* part = a.partials + b * a.ntiles * {nd};')
+        w.append(f'    double tot[{R}];')
+        w.append(f'    for (int r = 0; r < {R}; ++r) tot[r] = 0.0;')
+        for di, slot in enumerate(self.dyn_slots):
+            w.append(f'    tot[{slot}] = cfem::reduce_tiles<256>(part, '
+                     f'a.ntiles, {nd}, {di}, scratch, tid);')
+        w.append('    if (tid != 0) return;')
+        for fi, f in enumerate(self.funs):
+            if not f['is_objective']:
+                continue
+            spec = f['spec']
+            rows = f'(double)a.fun_rows[{fi}]'
+            const = []      # (slot, code, deps)
+            for e in spec.values:
+                for code, d in e.terms:
+                    if not (f['per_sample'] and self._is_sample_dep(f, d)):
+                        const.append((0, code, d))
+            for wrt in spec.wrt:
+                ref = f['args'][wrt]
+                if ref[0] != 'param':
+                    continue
+                for e in spec.jac.get(wrt, []):
+                    slot = self.slot_of[(ref[1], e.index[0])]
+                    for code, d in e.terms:
+                        if not (f['per_sample']
+                                and self._is_sample_dep(f, d)):
+                            const.append((slot, code, d))
+            if not const:
+                continue
+            deps = sorted({x for _, _, d in const for x in d})
+            defs, undefs = self._define_args(f, deps, 'global')
+            w.append(f'    // sample-independent terms of {f["name"]}')
+            w += defs
+            for slot, code, _ in const:
+                w.append(f'    tot[{slot}] += {rows} * ({code});')
+            w += undefs
+        w.append(f'    for (int r = 0; r < {R}; ++r) '
+                 f'a.reduce[b * {R} + r] = tot[r];')
+        w.append(f'    if (mask & {F}u) a.f[b] = tot[0];')
+        w.append(f'    if (mask & {GRAD}u) {{')
+        for i, s in enumerate(self.slots[1:], start=1):
+            w.append(f'        a.grad[b * a.ndec + a.var_off[{s["var"]}] + '
+                     f'{s["flat"]}] = tot[{i}];')
+        w.append('    }')
+        w.append('}')
+        w.append('')
+        w.append('__global__ void cfem_apply_reduced_kernel(const cfem::KArgs a, '
+                 'const double* __restrict__ red)')
+        w.append('{')
+        w.append('    const long long b = blockIdx.x;')
+        w.append('    if (threadIdx.x != 0) return;')
+        w.append(f'    a.f[b] = red[b * {R}];')
+        for i, s in enumerate(self.slots[1:], start=1):
+            w.append(f'    a.grad[b * a.ndec + a.var_off[{s["var"]}] + '
+                     f'{s["flat"]}] = red[b * {R} + {i}];')
+        w.append('}')
+        return '\n'.join(w)
+
+    def model_json(self):
+        st = self.st
+        return {
+            'abi': 1, 'tile': self.tile, 'masks': list(self.masks),
+            'vars': st.vars,
+            'data': [{k: d[k] for k in ('name', 'core', 'r0', 'hshift')}
+                     for d in st.data],
+            'scalars': st.scalars,
+            'funs': [{k: f[k] for k in ('name', 'is_objective', 'per_sample',
+                                        'r0', 'out_core', 'cons_index')}
+                     for f in st.funs],
+            'jac_blocks': [{'fun': b['fun'], 'wrt': b['wrt'], 'c': b['c']}
+                           for b in st.jac_blocks],
+            'hess_blocks': [{'fun': b['fun'], 'pair': list(b['pair']),
+                             'c': b['c']} for b in st.hess_blocks],
+            'reduce': [[s['var'], s['flat']] for s in self.slots],
+        }
+
+    def source(self):
+        st = self.st
+        kernels, smem = [], {}
+        for m in self.masks:
+            text, nbytes = self._emit_sample_kernel(m)
+            kernels.append(text)
+            smem[m] = nbytes
+        param_kernel = self._emit_param_kernel()
+        finalize = self._emit_finalize()
+        ncons = sum(1 for f in st.funs if not f['is_objective'])
+        mj = json.dumps(self.model_json(), sort_keys=True)
+        cstr = '\n'.join('    "' + mj[i:i + 100].replace('\\', '\\\\')
+                         .replace('"', '\\"') + '"'
+                         for i in range(0, len(mj), 100))
+
+        def table(ctype, name, rows):
+            body = ',\n'.join('    ' + r for r in rows) if rows else ''
+            n = max(1, len(rows))
+            if not rows:
+                body = '    {}'
+            return (f'constexpr {ctype} {name}[{n}] = {{\n{body}\n}};')
+
+        w = []
+        w.append('// GENERATED by colloc_fem_code_b200/codegen.py -- do not edit.')
+        w.append('// Model structure: ' + ', '.join(f['name'] for f in st.funs))
+        w.append(f'#define CFEM_TILE {self.tile}')
+        w.append('#include <cuda_runtime.h>')
+        w.append('#include <math.h>')
+        w.append('namespace gen {')
+        w.append('struct VarDesc { const char* name; int core; int per_sample; '
+                 'int r0; int hshift; };')
+        w.append('struct DataDesc { const char* name; int core; int r0; '
+                 'int hshift; };')
+        w.append('struct FunDesc { const char* name; int is_objective; '
+                 'int per_sample; int r0; int out_core; int cons_index; };')
+        w.append('struct BlockDesc { int fun; int c; };')
+        w.append(f'constexpr int kNumVars = {len(st.vars)};')
+        w.append(f'constexpr int kNumData = {len(st.data)};')
+        w.append(f'constexpr int kNumScalars = {len(st.scalars)};')
+        w.append(f'constexpr int kNumFuns = {len(st.funs)};')
+        w.append(f'constexpr int kNumCons = {ncons};')
+        w.append(f'constexpr int kNumJacBlocks = {len(st.jac_blocks)};')
+        w.append(f'constexpr int kNumHessBlocks = {len(st.hess_blocks)};')
+        w.append(f'constexpr int kNumReduce = {len(self.slots)};')
+        w.append(f'constexpr int kNumDynReduce = '
+                 f'{max(1, len(self.dyn_slots))};')
+        w.append(f'constexpr int kNumMasks = {len(self.masks)};')
+        w.append(table('VarDesc', 'kVars', [
+            f'{{"{v["name"]}", {v["core"]}, {v["per_sample"]}, {v["r0"]}, '
+            f'{v["hshift"]}}}' for v in st.vars]))
+        w.append(table('DataDesc', 'kData', [
+            f'{{"{d["name"]}", {d["core"]}, {d["r0"]}, {d["hshift"]}}}'
+            for d in st.data]))
+        w.append(table('FunDesc', 'kFuns', [
+            f'{{"{f["name"]}", {f["is_objective"]}, {f["per_sample"]}, '
+            f'{f["r0"]}, {f["out_core"]}, {f["cons_index"]}}}'
+            for f in st.funs]))
+        w.append(table('BlockDesc', 'kJacBlocks', [
+            f'{{{b["fun"]}, {b["c"]}}}' for b in st.jac_blocks]))
+        w.append(table('BlockDesc', 'kHessBlocks', [
+            f'{{{b["fun"]}, {b["c"]}}}' for b in st.hess_blocks]))
+        w.append('constexpr unsigned kMasks[] = {'
+                 + ', '.join(f'{m}u' for m in self.masks) + '};')
+        w.append('const char kModelJson[] =\n' + cstr + ';')
+        w.append('}  // namespace gen')
+        w.append('#include "cfem_device.cuh"')
+        w.append('namespace gen {')
+        w += kernels
+        w.append(param_kernel)
+        w.append(finalize)
+        w.append(f'constexpr int kNumParamEntries = {self.n_param_entries};')
+        # dispatchers
+        w.append('static cudaError_t configure_kernels()')
+        w.append('{')
+        w.append('    cudaError_t e = cudaSuccess;')
+        for m in self.masks:
+            if smem[m] > 48 * 1024:
+                w.append(f'    e = cudaFuncSetAttribute(cfem_sample_kernel_m{m}, '
+                         'cudaFuncAttributeMaxDynamicSharedMemorySize, '
+                         f'(int)kSmemBytes_m{m});')
+                w.append('    if (e != cudaSuccess) return e;')
+        w.append('    return e;')
+        w.append('}')
+        w.append('static cudaError_t launch_sample(unsigned mask, dim3 grid, '
+                 'cudaStream_t s, const cfem::KArgs& a)')
+        w.append('{')
+        w.append('    switch (mask) {')
+        for m in self.masks:
+            w.append(f'    case {m}u: cfem_sample_kernel_m{m}<<<grid, CFEM_TILE, '
+                     f'kSmemBytes_m{m}, s>>>(a); break;')
+        w.append('    default: return cudaErrorInvalidValue;')
+        w.append('    }')
+        w.append('    return cudaGetLastError();')
+        w.append('}')
+        w.append('static cudaError_t launch_param(unsigned mask, int batch, '
+                 'cudaStream_t s, const cfem::KArgs& a)')
+        w.append('{')
+        w.append('    const dim3 grid((kNumParamEntries + 63) / 64, batch);')
+        w.append('    cfem_param_kernel<<<grid, 64, 0, s>>>(a, mask);')
+        w.append('    return cudaGetLastError();')
+        w.append('}')
+        w.append('static cudaError_t launch_finalize(unsigned mask, int batch, '
+                 'cudaStream_t s, const cfem::KArgs& a)')
+        w.append('{')
+        w.append('    cfem_finalize_kernel<<<batch, 256, 0, s>>>(a, mask);')
+        w.append('    return cudaGetLastError();')
+        w.append('}')
+        w.append('static cudaError_t launch_apply_reduced(int batch, '
+                 'cudaStream_t s, const cfem::KArgs& a, const double* red)')
+        w.append('{')
+        w.append('    cfem_apply_reduced_kernel<<<batch, 32, 0, s>>>(a, red);')
+        w.append('    return cudaGetLastError();')
+        w.append('}')
+        w.append('}  // namespace gen')
+        w.append('#include "cfem_host.inl"')
+        return '\n'.join(w) + '\n'
+
+
+def generate(structure, **kwargs):
+    """CUDA source text for ``structure`` (an ``optim.Structure``)."""
+    return Generator(structure, **kwargs).source()

@@ -1,0 +1,203 @@
+// cfem_device.cuh -- hand-written device-side building blocks of the fused
+// per-sample evaluation kernels (FP64, sm_100a).
+//
+// A generated model translation unit (colloc_fem_code_b200/codegen.py) defines
+// the structure tables in namespace `gen` and CFEM_TILE, then includes this
+// header, then emits its kernels in terms of the helpers below:
+//
+//   stage_rows     coalesced global -> shared staging of a contiguous slab of
+//                  rows of a row-major [rows][CORE] array (the IPOPT-facing
+//                  decision vector keeps samples row-major, so the slab of one
+//                  tile -- including the one-sample halo that the N-1 row
+//                  functions read -- is ONE contiguous range of HBM);
+//   warp_put /     per-warp shared-memory transposition of the values one
+//   warp_flush     thread (= one sample) produces for a [rows][C] output block:
+//                  lanes park their C values in a conflict-free padded layout,
+//                  then the warp streams the 32*C contiguous doubles of the
+//                  block to HBM with unit-stride, full-sector stores;
+//   block_reduce   deterministic warp-shuffle + shared-memory tree reduction of
+//                  the per-thread objective / parameter-gradient partial sums.
+//
+// Reference being replaced: the NumPy broadcast evaluation of
+// /root/reference/symfem.py:50-65 (one temporary array per structural nonzero).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef CFEM_TILE
+#error "CFEM_TILE (threads per CTA == samples per tile) must be defined"
+#endif
+
+namespace cfem {
+
+constexpr unsigned kF = 1u, kGrad = 2u, kG = 4u, kJac = 8u, kHess = 16u;
+constexpr int kWarpsPerCta = CFEM_TILE / 32;
+
+template <int N> struct AtLeastOne { static constexpr int value = N > 0 ? N : 1; };
+
+// Kernel argument block: everything is resolved on the host at cfem_create().
+struct KArgs {
+    long long N;            // samples per problem
+    long long ntiles;       // ceil(N / CFEM_TILE)
+    long long ndec, ncons, nnz_jac, nnz_hess;   // per-problem strides
+    int       nreduce;      // reduction slots per tile
+    double    obj_factor;
+    const double* dvec;
+    const double* lam;
+    const double* data[AtLeastOne<gen::kNumData>::value];
+    long long     data_rows[AtLeastOne<gen::kNumData>::value];
+    double        scalars[AtLeastOne<gen::kNumScalars>::value];
+    double* f;
+    double* grad;
+    double* g;
+    double* jac;
+    double* hess;
+    double* partials;       // [batch][ntiles][nreduce]
+    double* reduce;         // [batch][nreduce]
+    long long var_off[AtLeastOne<gen::kNumVars>::value];
+    long long var_rows[AtLeastOne<gen::kNumVars>::value];
+    long long cons_off[AtLeastOne<gen::kNumCons>::value];
+    long long fun_rows[AtLeastOne<gen::kNumFuns>::value];
+    long long jac_off[AtLeastOne<gen::kNumJacBlocks>::value];
+    long long hess_off[AtLeastOne<gen::kNumHessBlocks>::value];
+};
+
+// ---------------------------------------------------------------------------
+// staging
+// ---------------------------------------------------------------------------
+
+// Copy `n` contiguous doubles (parameters) into shared memory.
+__device__ __forceinline__ void stage_contig(double* __restrict__ dst,
+                                             const double* __restrict__ src,
+                                             int n, int tid)
+{
+    for (int e = tid; e < n; e += CFEM_TILE) dst[e] = __ldg(src + e);
+}
+
+// Stage rows [row_begin, row_begin + NROWS) of a row-major [rows_total][CORE]
+// array into shared memory with row pitch PAD (odd pitch => the later
+// one-row-per-thread reads are bank-conflict free).  Rows outside the array
+// are skipped.  Global reads are unit-stride over the contiguous slab.
+template <int CORE, int PAD, int NROWS>
+__device__ __forceinline__ void stage_rows(double* __restrict__ dst,
+                                           const double* __restrict__ src,
+                                           long long rows_total,
+                                           long long row_begin, int tid)
+{
+    long long lo = row_begin < 0 ? 0 : row_begin;
+    long long hi = row_begin + NROWS;
+    if (hi > rows_total) hi = rows_total;
+    if (hi <= lo) return;
+    const int first = (int)(lo - row_begin);
+    const int nelem = (int)(hi - lo) * CORE;
+    const double* __restrict__ s = src + lo * CORE;
+    constexpr int kIter = (NROWS * CORE + CFEM_TILE - 1) / CFEM_TILE;
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+        const int e = tid + it * CFEM_TILE;
+        if (e < nelem) {
+            const int r = e / CORE, j = e - r * CORE;
+            dst[(first + r) * PAD + j] = __ldg(s + e);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// per-warp output transposition
+// ---------------------------------------------------------------------------
+
+constexpr int pad_odd(int c) { return c | 1; }
+
+// Lane parks its C values of one output block.
+template <int C>
+__device__ __forceinline__ void warp_put(double* __restrict__ wb, int lane,
+                                         const double (&v)[C])
+{
+#pragma unroll
+    for (int j = 0; j < C; ++j) wb[lane * pad_odd(C) + j] = v[j];
+}
+
+// The warp writes the first nvalid*C doubles of the block chunk to HBM,
+// consecutive lanes -> consecutive addresses.
+template <int C>
+__device__ __forceinline__ void warp_flush(const double* __restrict__ wb,
+                                           int lane, double* __restrict__ dst,
+                                           int nvalid)
+{
+    const int total = nvalid * C;
+#pragma unroll
+    for (int it = 0; it < C; ++it) {
+        const int e = lane + it * 32;
+        if (e < total) {
+            const int t = e / C, j = e - t * C;
+            __stcs(dst + e, wb[t * pad_odd(C) + j]);
+        }
+    }
+}
+
+// C == 1 blocks are already unit stride: no staging needed.
+__device__ __forceinline__ void lane_store(double* __restrict__ dst, int lane,
+                                           int nvalid, double v)
+{
+    if (lane < nvalid) __stcs(dst + lane, v);
+}
+
+// ---------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+        v += __shfl_down_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Deterministic CTA reduction of R per-thread values; thread 0 writes out[r].
+// `scratch` holds kWarpsPerCta * R doubles.
+template <int R>
+__device__ __forceinline__ void block_reduce_store(const double (&v)[R],
+                                                   double* __restrict__ scratch,
+                                                   double* __restrict__ out,
+                                                   int tid)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double s = warp_sum(v[r]);
+        if (lane == 0) scratch[warp * R + r] = s;
+    }
+    __syncthreads();
+    if (tid < R) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; ++w) s += scratch[w * R + tid];
+        out[tid] = s;
+    }
+}
+
+// Fixed-order sum over tiles of one reduction slot (one CTA per problem).
+template <int THREADS>
+__device__ __forceinline__ double reduce_tiles(const double* __restrict__ part,
+                                               long long ntiles, int nreduce,
+                                               int slot, double* scratch,
+                                               int tid)
+{
+    double s = 0.0;
+    for (long long t = tid; t < ntiles; t += THREADS)
+        s += part[t * nreduce + slot];
+    s = warp_sum(s);
+    __syncthreads();
+    if ((tid & 31) == 0) scratch[tid >> 5] = s;
+    __syncthreads();
+    double tot = 0.0;
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) tot += scratch[w];
+    }
+    return tot;     // valid in thread 0
+}
+
+}  // namespace cfem

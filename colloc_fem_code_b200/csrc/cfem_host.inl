@@ -1,0 +1,527 @@
+// cfem_host.inl -- hand-written host side of the C ABI declared in
+// include/cfem.h.  Included at the END of every generated model translation
+// unit, after namespace `gen` has defined the structure tables, the kernels and
+// the launch_* dispatchers.  No torch, no C++ types across the boundary.
+//
+// Memory model: all problem arrays live in HBM for the life of the handle
+// (cudaMalloc once in cfem_create); the decision vector, the multipliers and
+// the results keep the IPOPT-facing order, so a callback is one H2D copy of
+// dvec (and lambda), the fused kernels, and one D2H copy per requested result.
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+
+#include "cfem.h"
+
+struct cfem_problem {
+    int           device = 0;
+    cudaStream_t  stream = nullptr;
+    bool          own_stream = false;
+    long long     N = 0;
+    int           batch = 1;
+    int           halo = 0;
+    cfem::KArgs   k;
+    double*       d_dvec = nullptr;     // owned copy of dvec (k.dvec may alias it)
+    double*       d_lam = nullptr;
+    double*       d_data[cfem::AtLeastOne<gen::kNumData>::value] = {};
+    bool          have_dvec = false;
+    bool          have_lam = false;
+    unsigned      valid = 0;
+    cudaEvent_t   ev[16] = {};
+    long long     launches = 0;
+    void*         flush_buf = nullptr;
+    size_t        flush_bytes = 0;
+    std::string   err;
+};
+
+namespace cfem {
+
+static thread_local std::string g_create_error;
+
+static int fail(cfem_problem* p, int code, const char* what, cudaError_t e)
+{
+    char buf[512];
+    if (e != cudaSuccess)
+        snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else
+        snprintf(buf, sizeof buf, "%s", what);
+    if (p) p->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CFEM_CUDA(p, call)                                                    \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return cfem::fail((p), CFEM_ECUDA, #call, e_); \
+    } while (0)
+
+struct Layout {
+    long long ndec, ncons, nnz_jac, nnz_hess;
+    long long var_off[AtLeastOne<gen::kNumVars>::value];
+    long long var_rows[AtLeastOne<gen::kNumVars>::value];
+    long long cons_off[AtLeastOne<gen::kNumCons>::value];
+    long long fun_rows[AtLeastOne<gen::kNumFuns>::value];
+    long long jac_off[AtLeastOne<gen::kNumJacBlocks>::value];
+    long long hess_off[AtLeastOne<gen::kNumHessBlocks>::value];
+    long long data_rows[AtLeastOne<gen::kNumData>::value];
+};
+
+// The layout is a pure function of (N, halo): prefix sums over the tables in
+// registration order (cf. /root/reference/fem.py:36-57 for the order).
+static void compute_layout(long long N, int halo, Layout& L)
+{
+    long long off = 0;
+    for (int v = 0; v < gen::kNumVars; ++v) {
+        const gen::VarDesc& d = gen::kVars[v];
+        const long long rows = d.per_sample ? N + d.r0 + (long long)halo * d.hshift : 1;
+        L.var_off[v] = off;
+        L.var_rows[v] = rows;
+        off += rows * d.core;
+    }
+    L.ndec = off;
+    for (int i = 0; i < gen::kNumData; ++i)
+        L.data_rows[i] = N + gen::kData[i].r0 + (long long)halo * gen::kData[i].hshift;
+    long long coff = 0;
+    for (int f = 0; f < gen::kNumFuns; ++f) {
+        const gen::FunDesc& d = gen::kFuns[f];
+        long long rows = 1;
+        if (d.per_sample) {
+            long long adj = d.r0 + halo;
+            rows = N + (adj < 0 ? adj : 0);
+        }
+        L.fun_rows[f] = rows;
+        if (d.cons_index >= 0) {
+            L.cons_off[d.cons_index] = coff;
+            coff += rows * d.out_core;
+        }
+    }
+    L.ncons = coff;
+    long long joff = 0;
+    for (int b = 0; b < gen::kNumJacBlocks; ++b) {
+        L.jac_off[b] = joff;
+        joff += L.fun_rows[gen::kJacBlocks[b].fun] * gen::kJacBlocks[b].c;
+    }
+    L.nnz_jac = joff;
+    long long hoff = 0;
+    for (int b = 0; b < gen::kNumHessBlocks; ++b) {
+        L.hess_off[b] = hoff;
+        hoff += L.fun_rows[gen::kHessBlocks[b].fun] * gen::kHessBlocks[b].c;
+    }
+    L.nnz_hess = hoff;
+}
+
+static unsigned pick_mask(unsigned what)
+{
+    // smallest instantiated superset of `what`
+    unsigned best = 0;
+    int best_bits = 99;
+    for (int i = 0; i < gen::kNumMasks; ++i) {
+        const unsigned m = gen::kMasks[i];
+        if ((m & what) != what) continue;
+        const int bits = __builtin_popcount(m);
+        if (bits < best_bits) { best = m; best_bits = bits; }
+    }
+    return best;
+}
+
+}  // namespace cfem
+
+extern "C" {
+
+int cfem_abi_version(void) { return CFEM_ABI_VERSION; }
+
+const char* cfem_model_json(void) { return gen::kModelJson; }
+
+int cfem_model_sizes(int64_t n_samples, int32_t halo, int64_t* ndec,
+                     int64_t* ncons, int64_t* nnz_jac, int64_t* nnz_hess)
+{
+    if (n_samples < 2 || halo < 0 || halo > 1) return CFEM_EINVAL;
+    cfem::Layout L;
+    cfem::compute_layout(n_samples, halo, L);
+    if (ndec) *ndec = L.ndec;
+    if (ncons) *ncons = L.ncons;
+    if (nnz_jac) *nnz_jac = L.nnz_jac;
+    if (nnz_hess) *nnz_hess = L.nnz_hess;
+    return CFEM_OK;
+}
+
+const char* cfem_last_error(const cfem_problem* p)
+{
+    return p ? p->err.c_str() : cfem::g_create_error.c_str();
+}
+
+void cfem_destroy(cfem_problem* p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    cudaFree(p->d_dvec);
+    cudaFree(p->d_lam);
+    for (int i = 0; i < gen::kNumData; ++i) cudaFree(p->d_data[i]);
+    cudaFree(p->k.f);
+    cudaFree(p->k.grad);
+    cudaFree(p->k.g);
+    cudaFree(p->k.jac);
+    cudaFree(p->k.hess);
+    cudaFree(p->k.partials);
+    cudaFree(p->k.reduce);
+    cudaFree(p->flush_buf);
+    for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
+                int32_t halo, const double* const* data, int32_t n_data,
+                const double* scalars, int32_t n_scalars, int32_t device)
+{
+    if (!out) return CFEM_EINVAL;
+    *out = nullptr;
+    if (n_samples < 2 || batch < 1 || halo < 0 || halo > 1)
+        return cfem::fail(nullptr, CFEM_EINVAL,
+                          "cfem_create: need n_samples >= 2, batch >= 1, halo in {0,1}",
+                          cudaSuccess);
+    if (n_data != gen::kNumData || n_scalars != gen::kNumScalars ||
+        (n_data > 0 && !data) || (n_scalars > 0 && !scalars))
+        return cfem::fail(nullptr, CFEM_EINVAL,
+                          "cfem_create: data/scalar count does not match the model",
+                          cudaSuccess);
+    int ndev = 0;
+    CFEM_CUDA(nullptr, cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev)
+        return cfem::fail(nullptr, CFEM_EINVAL, "cfem_create: no such CUDA device",
+                          cudaSuccess);
+    CFEM_CUDA(nullptr, cudaSetDevice(device));
+    cudaError_t ce = gen::configure_kernels();
+    if (ce != cudaSuccess)
+        return cfem::fail(nullptr, CFEM_ECUDA, "configure_kernels", ce);
+
+    cfem_problem* p = new (std::nothrow) cfem_problem();
+    if (!p) return cfem::fail(nullptr, CFEM_ENOMEM, "cfem_create: host allocation", cudaSuccess);
+    p->device = device;
+    p->N = n_samples;
+    p->batch = batch;
+    p->halo = halo;
+
+    cfem::Layout L;
+    cfem::compute_layout(n_samples, halo, L);
+    cfem::KArgs& k = p->k;
+    memset(&k, 0, sizeof k);
+    k.N = n_samples;
+    k.ntiles = (n_samples + CFEM_TILE - 1) / CFEM_TILE;
+    k.ndec = L.ndec; k.ncons = L.ncons; k.nnz_jac = L.nnz_jac; k.nnz_hess = L.nnz_hess;
+    k.nreduce = gen::kNumReduce;
+    k.obj_factor = 1.0;
+    memcpy(k.var_off, L.var_off, sizeof L.var_off);
+    memcpy(k.var_rows, L.var_rows, sizeof L.var_rows);
+    memcpy(k.cons_off, L.cons_off, sizeof L.cons_off);
+    memcpy(k.fun_rows, L.fun_rows, sizeof L.fun_rows);
+    memcpy(k.jac_off, L.jac_off, sizeof L.jac_off);
+    memcpy(k.hess_off, L.hess_off, sizeof L.hess_off);
+    memcpy(k.data_rows, L.data_rows, sizeof L.data_rows);
+    for (int i = 0; i < gen::kNumScalars; ++i) k.scalars[i] = scalars[i];
+
+#define CFEM_TRY(call)                                                     \
+    do {                                                                   \
+        cudaError_t e_ = (call);                                           \
+        if (e_ != cudaSuccess) {                                           \
+            int rc_ = cfem::fail(nullptr, e_ == cudaErrorMemoryAllocation  \
+                                     ? CFEM_ENOMEM : CFEM_ECUDA, #call, e_); \
+            cfem_destroy(p);                                               \
+            return rc_;                                                    \
+        }                                                                  \
+    } while (0)
+
+    const size_t B = (size_t)batch, D = sizeof(double);
+    CFEM_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    p->own_stream = true;
+    for (cudaEvent_t& e : p->ev) CFEM_TRY(cudaEventCreate(&e));
+    CFEM_TRY(cudaMalloc(&p->d_dvec, B * L.ndec * D));
+    CFEM_TRY(cudaMalloc(&p->d_lam, B * (L.ncons > 0 ? L.ncons : 1) * D));
+    CFEM_TRY(cudaMalloc(&k.f, B * D));
+    CFEM_TRY(cudaMalloc(&k.grad, B * L.ndec * D));
+    CFEM_TRY(cudaMalloc(&k.g, B * (L.ncons > 0 ? L.ncons : 1) * D));
+    CFEM_TRY(cudaMalloc(&k.jac, B * (L.nnz_jac > 0 ? L.nnz_jac : 1) * D));
+    CFEM_TRY(cudaMalloc(&k.hess, B * (L.nnz_hess > 0 ? L.nnz_hess : 1) * D));
+    CFEM_TRY(cudaMalloc(&k.partials, B * k.ntiles * gen::kNumDynReduce * D));
+    CFEM_TRY(cudaMalloc(&k.reduce, B * gen::kNumReduce * D));
+    // structurally-zero gradient entries are written once, here
+    CFEM_TRY(cudaMemset(k.grad, 0, B * L.ndec * D));
+    CFEM_TRY(cudaMemset(k.reduce, 0, B * gen::kNumReduce * D));
+    CFEM_TRY(cudaMemset(k.f, 0, B * D));
+    for (int i = 0; i < gen::kNumData; ++i) {
+        const size_t n = B * L.data_rows[i] * gen::kData[i].core;
+        if (!data[i]) {
+            cfem::fail(nullptr, CFEM_EINVAL, "cfem_create: null data array", cudaSuccess);
+            cfem_destroy(p);
+            return CFEM_EINVAL;
+        }
+        CFEM_TRY(cudaMalloc(&p->d_data[i], n * D));
+        CFEM_TRY(cudaMemcpy(p->d_data[i], data[i], n * D, cudaMemcpyHostToDevice));
+        k.data[i] = p->d_data[i];
+    }
+#undef CFEM_TRY
+    k.dvec = p->d_dvec;
+    k.lam = p->d_lam;
+    *out = p;
+    return CFEM_OK;
+}
+
+int cfem_set_stream(cfem_problem* p, void* cuda_stream)
+{
+    if (!p) return CFEM_EINVAL;
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    CFEM_CUDA(p, cudaStreamSynchronize(p->stream));
+    if (p->own_stream) { cudaStreamDestroy(p->stream); p->own_stream = false; }
+    if (cuda_stream) {
+        p->stream = (cudaStream_t)cuda_stream;
+    } else {
+        CFEM_CUDA(p, cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+        p->own_stream = true;
+    }
+    return CFEM_OK;
+}
+
+int cfem_sizes(const cfem_problem* p, int64_t* ndec, int64_t* ncons,
+               int64_t* nnz_jac, int64_t* nnz_hess)
+{
+    if (!p) return CFEM_EINVAL;
+    if (ndec) *ndec = p->k.ndec;
+    if (ncons) *ncons = p->k.ncons;
+    if (nnz_jac) *nnz_jac = p->k.nnz_jac;
+    if (nnz_hess) *nnz_hess = p->k.nnz_hess;
+    return CFEM_OK;
+}
+
+int cfem_layout(const cfem_problem* p, int64_t* var_offset, int64_t* cons_offset,
+                int64_t* jac_offset, int64_t* hess_offset, int64_t* fun_rows)
+{
+    if (!p) return CFEM_EINVAL;
+    const cfem::KArgs& k = p->k;
+    if (var_offset) for (int i = 0; i < gen::kNumVars; ++i) var_offset[i] = k.var_off[i];
+    if (cons_offset) for (int i = 0; i < gen::kNumCons; ++i) cons_offset[i] = k.cons_off[i];
+    if (jac_offset) for (int i = 0; i < gen::kNumJacBlocks; ++i) jac_offset[i] = k.jac_off[i];
+    if (hess_offset) for (int i = 0; i < gen::kNumHessBlocks; ++i) hess_offset[i] = k.hess_off[i];
+    if (fun_rows) for (int i = 0; i < gen::kNumFuns; ++i) fun_rows[i] = k.fun_rows[i];
+    return CFEM_OK;
+}
+
+int cfem_set_dvec(cfem_problem* p, const double* dvec_host)
+{
+    if (!p || !dvec_host) return CFEM_EINVAL;
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    CFEM_CUDA(p, cudaMemcpyAsync(p->d_dvec, dvec_host,
+                                 (size_t)p->batch * p->k.ndec * sizeof(double),
+                                 cudaMemcpyHostToDevice, p->stream));
+    p->k.dvec = p->d_dvec;
+    p->have_dvec = true;
+    p->valid = 0;
+    return CFEM_OK;
+}
+
+int cfem_set_dvec_device(cfem_problem* p, const double* dvec_dev)
+{
+    if (!p || !dvec_dev) return CFEM_EINVAL;
+    p->k.dvec = dvec_dev;       // adopted, not copied: inputs stay where they are
+    p->have_dvec = true;
+    p->valid = 0;
+    return CFEM_OK;
+}
+
+int cfem_set_multipliers(cfem_problem* p, double obj_factor, const double* lambda_host)
+{
+    if (!p || (!lambda_host && p->k.ncons > 0)) return CFEM_EINVAL;
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    if (p->k.ncons > 0)
+        CFEM_CUDA(p, cudaMemcpyAsync(p->d_lam, lambda_host,
+                                     (size_t)p->batch * p->k.ncons * sizeof(double),
+                                     cudaMemcpyHostToDevice, p->stream));
+    p->k.lam = p->d_lam;
+    p->k.obj_factor = obj_factor;
+    p->have_lam = true;
+    p->valid &= ~CFEM_HESS;
+    return CFEM_OK;
+}
+
+int cfem_set_multipliers_device(cfem_problem* p, double obj_factor, const double* lambda_dev)
+{
+    if (!p || (!lambda_dev && p->k.ncons > 0)) return CFEM_EINVAL;
+    p->k.lam = lambda_dev;
+    p->k.obj_factor = obj_factor;
+    p->have_lam = true;
+    p->valid &= ~CFEM_HESS;
+    return CFEM_OK;
+}
+
+int cfem_eval(cfem_problem* p, uint32_t what)
+{
+    if (!p || what == 0 || (what & ~CFEM_ALL)) return CFEM_EINVAL;
+    if (!p->have_dvec)
+        return cfem::fail(p, CFEM_ESTATE, "cfem_eval: no decision vector set", cudaSuccess);
+    if ((what & CFEM_HESS) && !p->have_lam)
+        return cfem::fail(p, CFEM_ESTATE, "cfem_eval: no multipliers set", cudaSuccess);
+    const unsigned mask = cfem::pick_mask(what);
+    if (!mask) return cfem::fail(p, CFEM_EINVAL, "cfem_eval: no kernel for this selector", cudaSuccess);
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    const dim3 grid((unsigned)p->k.ntiles, (unsigned)p->batch);
+    CFEM_CUDA(p, gen::launch_sample(mask, grid, p->stream, p->k));
+    p->launches += 1;
+    if (gen::kNumParamEntries > 0 && (mask & (CFEM_G | CFEM_JAC | CFEM_HESS))) {
+        CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->stream, p->k));
+        p->launches += 1;
+    }
+    if (mask & (CFEM_F | CFEM_GRAD)) {
+        CFEM_CUDA(p, gen::launch_finalize(mask, p->batch, p->stream, p->k));
+        p->launches += 1;
+    }
+    p->valid |= mask;
+    return CFEM_OK;
+}
+
+int cfem_fetch(cfem_problem* p, uint32_t which, double* host_out)
+{
+    if (!p || !host_out) return CFEM_EINVAL;
+    const double* src = nullptr;
+    size_t n = 0;
+    const size_t B = (size_t)p->batch;
+    switch (which) {
+        case CFEM_F:    src = p->k.f;    n = B; break;
+        case CFEM_GRAD: src = p->k.grad; n = B * p->k.ndec; break;
+        case CFEM_G:    src = p->k.g;    n = B * p->k.ncons; break;
+        case CFEM_JAC:  src = p->k.jac;  n = B * p->k.nnz_jac; break;
+        case CFEM_HESS: src = p->k.hess; n = B * p->k.nnz_hess; break;
+        default: return CFEM_EINVAL;
+    }
+    if (!(p->valid & which))
+        return cfem::fail(p, CFEM_ESTATE, "cfem_fetch: result not evaluated", cudaSuccess);
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    if (n)
+        CFEM_CUDA(p, cudaMemcpyAsync(host_out, src, n * sizeof(double),
+                                     cudaMemcpyDeviceToHost, p->stream));
+    CFEM_CUDA(p, cudaStreamSynchronize(p->stream));
+    return CFEM_OK;
+}
+
+static int cfem_eval_fetch(cfem_problem* p, uint32_t which, double* out)
+{
+    if (!p) return CFEM_EINVAL;
+    if (!(p->valid & which)) {
+        int rc = cfem_eval(p, which);
+        if (rc) return rc;
+    }
+    return cfem_fetch(p, which, out);
+}
+
+int cfem_eval_f(cfem_problem* p, double* f) { return cfem_eval_fetch(p, CFEM_F, f); }
+int cfem_eval_grad_f(cfem_problem* p, double* grad) { return cfem_eval_fetch(p, CFEM_GRAD, grad); }
+int cfem_eval_g(cfem_problem* p, double* g) { return cfem_eval_fetch(p, CFEM_G, g); }
+int cfem_eval_jac_values(cfem_problem* p, double* values) { return cfem_eval_fetch(p, CFEM_JAC, values); }
+
+int cfem_eval_hess_values(cfem_problem* p, double obj_factor, const double* lambda, double* values)
+{
+    int rc = cfem_set_multipliers(p, obj_factor, lambda);
+    if (rc) return rc;
+    return cfem_eval_fetch(p, CFEM_HESS, values);
+}
+
+int cfem_device_ptrs(cfem_problem* p, double** dvec, double** lambda, double** f,
+                     double** grad, double** g, double** jac, double** hess,
+                     double** reduce)
+{
+    if (!p) return CFEM_EINVAL;
+    if (dvec) *dvec = p->d_dvec;
+    if (lambda) *lambda = p->d_lam;
+    if (f) *f = p->k.f;
+    if (grad) *grad = p->k.grad;
+    if (g) *g = p->k.g;
+    if (jac) *jac = p->k.jac;
+    if (hess) *hess = p->k.hess;
+    if (reduce) *reduce = p->k.reduce;
+    return CFEM_OK;
+}
+
+int cfem_apply_reduced(cfem_problem* p, const double* reduce_dev)
+{
+    if (!p || !reduce_dev) return CFEM_EINVAL;
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    CFEM_CUDA(p, gen::launch_apply_reduced(p->batch, p->stream, p->k, reduce_dev));
+    p->launches += 1;
+    return CFEM_OK;
+}
+
+int cfem_synchronize(cfem_problem* p)
+{
+    if (!p) return CFEM_EINVAL;
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    CFEM_CUDA(p, cudaStreamSynchronize(p->stream));
+    return CFEM_OK;
+}
+
+int cfem_event_record(cfem_problem* p, int32_t slot)
+{
+    if (!p || slot < 0 || slot >= 16) return CFEM_EINVAL;
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    CFEM_CUDA(p, cudaEventRecord(p->ev[slot], p->stream));
+    return CFEM_OK;
+}
+
+int cfem_event_elapsed_ms(cfem_problem* p, int32_t start_slot, int32_t stop_slot, float* ms)
+{
+    if (!p || !ms || start_slot < 0 || start_slot >= 16 || stop_slot < 0 || stop_slot >= 16)
+        return CFEM_EINVAL;
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    CFEM_CUDA(p, cudaEventSynchronize(p->ev[stop_slot]));
+    CFEM_CUDA(p, cudaEventElapsedTime(ms, p->ev[start_slot], p->ev[stop_slot]));
+    return CFEM_OK;
+}
+
+int64_t cfem_launch_count(const cfem_problem* p) { return p ? p->launches : -1; }
+
+int cfem_flush_l2(cfem_problem* p, size_t bytes)
+{
+    if (!p || bytes == 0) return CFEM_EINVAL;
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    if (bytes > p->flush_bytes) {
+        cudaFree(p->flush_buf);
+        p->flush_buf = nullptr;
+        p->flush_bytes = 0;
+        CFEM_CUDA(p, cudaMalloc(&p->flush_buf, bytes));
+        p->flush_bytes = bytes;
+    }
+    CFEM_CUDA(p, cudaMemsetAsync(p->flush_buf, 0, bytes, p->stream));
+    return CFEM_OK;
+}
+
+void* cfem_host_alloc(size_t bytes)
+{
+    void* ptr = nullptr;
+    if (cudaHostAlloc(&ptr, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return ptr;
+}
+
+void cfem_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
+int cfem_host_register(void* ptr, size_t bytes)
+{
+    if (!ptr || !bytes) return CFEM_EINVAL;
+    if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return CFEM_ECUDA;
+    }
+    return CFEM_OK;
+}
+
+int cfem_host_unregister(void* ptr)
+{
+    if (!ptr) return CFEM_EINVAL;
+    if (cudaHostUnregister(ptr) != cudaSuccess) { cudaGetLastError(); return CFEM_ECUDA; }
+    return CFEM_OK;
+}
+
+}  // extern "C"
