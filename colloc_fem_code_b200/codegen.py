@@ -438,33 +438,50 @@ class Generator:
                                    f'({mult}) * ({e.code})'))
         return ents
 
+    #: entries per __noinline__ chunk function of the parameter kernel (ptxas
+    #: time grows super-linearly with the size of one function)
+    PARAM_CHUNK = 32
+
     def _emit_param_kernel(self):
         ents = self._param_entries()
         order = ents[G] + ents[JAC] + ents[HESS]
         n_g, n_j = len(ents[G]), len(ents[JAC])
         self.n_param_entries = len(order)
+        CH = self.PARAM_CHUNK
         w = []
+        nchunks = (len(order) + CH - 1) // CH
+        for c in range(nchunks):
+            w.append(f'static __device__ __noinline__ void cfem_param_chunk{c}('
+                     'const cfem::KArgs& a, const long long b, const int e)')
+            w.append('{')
+            w.append('    const double* __restrict__ dvec = a.dvec + b * a.ndec;')
+            w.append('    const double* __restrict__ lam = a.lam + b * a.ncons;')
+            w.append('    (void)dvec; (void)lam;')
+            w.append('    switch (e) {')
+            for i in range(c * CH, min(len(order), (c + 1) * CH)):
+                f, deps, dest, code = order[i]
+                w.append(f'    case {i}: {{')
+                defs, undefs = self._define_args(f, deps, 'global')
+                w += defs
+                w.append(f'        {dest} = {code};')
+                w += undefs
+                w.append('        break; }')
+            w.append('    default: break;')
+            w.append('    }')
+            w.append('}')
         w.append('__global__ void __launch_bounds__(64)')
         w.append('cfem_param_kernel(const cfem::KArgs a, const unsigned mask)')
         w.append('{')
         w.append('    const int e = blockIdx.x * 64 + threadIdx.x;')
         w.append('    const long long b = blockIdx.y;')
-        w.append('    const double* __restrict__ dvec = a.dvec + b * a.ndec;')
-        w.append('    const double* __restrict__ lam = a.lam + b * a.ncons;')
-        w.append('    (void)dvec; (void)lam;')
         w.append(f'    if (e >= {len(order)}) return;')
         w.append(f'    if (e < {n_g}) {{ if (!(mask & {G}u)) return; }}')
         w.append(f'    else if (e < {n_g + n_j}) '
                  f'{{ if (!(mask & {JAC}u)) return; }}')
         w.append(f'    else {{ if (!(mask & {HESS}u)) return; }}')
-        w.append('    switch (e) {')
-        for i, (f, deps, dest, code) in enumerate(order):
-            w.append(f'    case {i}: {{')
-            defs, undefs = self._define_args(f, deps, 'global')
-            w += defs
-            w.append(f'        {dest} = {code};')
-            w += undefs
-            w.append('        break; }')
+        w.append(f'    switch (e / {CH}) {{')
+        for c in range(nchunks):
+            w.append(f'    case {c}: cfem_param_chunk{c}(a, b, e); break;')
         w.append('    default: break;')
         w.append('    }')
         w.append('}')
@@ -557,34 +574,17 @@ class Generator:
             'reduce': [[s['var'], s['flat']] for s in self.slots],
         }
 
-    def source(self):
+    def _tables(self):
+        """Structure tables of namespace ``gen`` (shared by both units)."""
         st = self.st
-        kernels, smem = [], {}
-        for m in self.masks:
-            text, nbytes = self._emit_sample_kernel(m)
-            kernels.append(text)
-            smem[m] = nbytes
-        param_kernel = self._emit_param_kernel()
-        finalize = self._emit_finalize()
         ncons = sum(1 for f in st.funs if not f['is_objective'])
-        mj = json.dumps(self.model_json(), sort_keys=True)
-        cstr = '\n'.join('    "' + mj[i:i + 100].replace('\\', '\\\\')
-                         .replace('"', '\\"') + '"'
-                         for i in range(0, len(mj), 100))
 
         def table(ctype, name, rows):
-            body = ',\n'.join('    ' + r for r in rows) if rows else ''
-            n = max(1, len(rows))
-            if not rows:
-                body = '    {}'
-            return (f'constexpr {ctype} {name}[{n}] = {{\n{body}\n}};')
+            body = ',\n'.join('    ' + r for r in rows) if rows else '    {}'
+            return (f'constexpr {ctype} {name}[{max(1, len(rows))}] = '
+                    f'{{\n{body}\n}};')
 
         w = []
-        w.append('// GENERATED by colloc_fem_code_b200/codegen.py -- do not edit.')
-        w.append('// Model structure: ' + ', '.join(f['name'] for f in st.funs))
-        w.append(f'#define CFEM_TILE {self.tile}')
-        w.append('#include <cuda_runtime.h>')
-        w.append('#include <math.h>')
         w.append('namespace gen {')
         w.append('struct VarDesc { const char* name; int core; int per_sample; '
                  'int r0; int hshift; };')
@@ -620,15 +620,66 @@ class Generator:
             f'{{{b["fun"]}, {b["c"]}}}' for b in st.hess_blocks]))
         w.append('constexpr unsigned kMasks[] = {'
                  + ', '.join(f'{m}u' for m in self.masks) + '};')
+        w.append('}  // namespace gen')
+        return w
+
+    def sources(self):
+        """``{'main': ..., 'param': ...}``: the two translation units of one
+        model library.  ``param`` holds only the parameter-only constraint
+        kernel (long straight-line code, slow to compile, depends on nothing
+        hand-written but cfem_args.cuh); ``main`` holds the per-sample
+        kernels, the reductions and the host side of the C ABI."""
+        st = self.st
+        kernels, smem = [], {}
+        for m in self.masks:
+            text, nbytes = self._emit_sample_kernel(m)
+            kernels.append(text)
+            smem[m] = nbytes
+        param_kernel = self._emit_param_kernel()
+        finalize = self._emit_finalize()
+        mj = json.dumps(self.model_json(), sort_keys=True)
+        cstr = '\n'.join('    "' + mj[i:i + 100].replace('\\', '\\\\')
+                         .replace('"', '\\"') + '"'
+                         for i in range(0, len(mj), 100))
+        head = ['// GENERATED by colloc_fem_code_b200/codegen.py -- do not edit.',
+                '// Model structure: ' + ', '.join(f['name'] for f in st.funs),
+                '#include <cuda_runtime.h>', '#include <math.h>']
+        tables = self._tables()
+        launch_param_sig = ('cudaError_t launch_param(unsigned mask, int batch, '
+                            'cudaStream_t s, const cfem::KArgs& a)')
+
+        # ---- parameter-only unit
+        w = list(head) + tables
+        w.append('#include "cfem_args.cuh"')
+        w.append('namespace gen {')
+        w.append(param_kernel)
+        w.append(launch_param_sig)
+        w.append('{')
+        if self.n_param_entries:
+            w.append(f'    const dim3 grid(({self.n_param_entries} + 63) / 64, '
+                     'batch);')
+            w.append('    cfem_param_kernel<<<grid, 64, 0, s>>>(a, mask);')
+            w.append('    return cudaGetLastError();')
+        else:
+            w.append('    (void)mask; (void)batch; (void)s; (void)a;')
+            w.append('    return cudaSuccess;')
+        w.append('}')
+        w.append('}  // namespace gen')
+        param_unit = '\n'.join(w) + '\n'
+
+        # ---- main unit
+        w = list(head)
+        w.append(f'#define CFEM_TILE {self.tile}')
+        w += tables
+        w.append('namespace gen {')
         w.append('const char kModelJson[] =\n' + cstr + ';')
         w.append('}  // namespace gen')
         w.append('#include "cfem_device.cuh"')
         w.append('namespace gen {')
         w += kernels
-        w.append(param_kernel)
         w.append(finalize)
         w.append(f'constexpr int kNumParamEntries = {self.n_param_entries};')
-        # dispatchers
+        w.append(launch_param_sig + ';    // parameter-only unit')
         w.append('static cudaError_t configure_kernels()')
         w.append('{')
         w.append('    cudaError_t e = cudaSuccess;')
@@ -651,13 +702,6 @@ class Generator:
         w.append('    }')
         w.append('    return cudaGetLastError();')
         w.append('}')
-        w.append('static cudaError_t launch_param(unsigned mask, int batch, '
-                 'cudaStream_t s, const cfem::KArgs& a)')
-        w.append('{')
-        w.append('    const dim3 grid((kNumParamEntries + 63) / 64, batch);')
-        w.append('    cfem_param_kernel<<<grid, 64, 0, s>>>(a, mask);')
-        w.append('    return cudaGetLastError();')
-        w.append('}')
         w.append('static cudaError_t launch_finalize(unsigned mask, int batch, '
                  'cudaStream_t s, const cfem::KArgs& a)')
         w.append('{')
@@ -672,9 +716,9 @@ class Generator:
         w.append('}')
         w.append('}  // namespace gen')
         w.append('#include "cfem_host.inl"')
-        return '\n'.join(w) + '\n'
+        return {'main': '\n'.join(w) + '\n', 'param': param_unit}
 
 
 def generate(structure, **kwargs):
-    """CUDA source text for ``structure`` (an ``optim.Structure``)."""
-    return Generator(structure, **kwargs).source()
+    """CUDA sources ``{'main', 'param'}`` for an ``optim.Structure``."""
+    return Generator(structure, **kwargs).sources()

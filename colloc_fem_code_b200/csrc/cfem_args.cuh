@@ -1,0 +1,39 @@
+// cfem_args.cuh -- the kernel argument block shared by every kernel of a
+// generated model library.  Included after namespace `gen` has defined the
+// structure-table sizes (kNumVars, kNumData, ...).  Kept in its own header so
+// that the (slow to compile) parameter-only kernel translation unit depends on
+// nothing else that is hand-written.
+#pragma once
+
+namespace cfem {
+
+template <int N> struct AtLeastOne { static constexpr int value = N > 0 ? N : 1; };
+
+// Kernel argument block: everything is resolved on the host at cfem_create().
+struct KArgs {
+    long long N;            // samples per problem
+    long long ntiles;       // ceil(N / CFEM_TILE)
+    long long ndec, ncons, nnz_jac, nnz_hess;   // per-problem strides
+    int       nreduce;      // reduction slots per tile
+    double    obj_factor;
+    const double* dvec;
+    const double* lam;
+    const double* data[AtLeastOne<gen::kNumData>::value];
+    long long     data_rows[AtLeastOne<gen::kNumData>::value];
+    double        scalars[AtLeastOne<gen::kNumScalars>::value];
+    double* f;
+    double* grad;
+    double* g;
+    double* jac;
+    double* hess;
+    double* partials;       // [batch][ntiles][nreduce]
+    double* reduce;         // [batch][nreduce]
+    long long var_off[AtLeastOne<gen::kNumVars>::value];
+    long long var_rows[AtLeastOne<gen::kNumVars>::value];
+    long long cons_off[AtLeastOne<gen::kNumCons>::value];
+    long long fun_rows[AtLeastOne<gen::kNumFuns>::value];
+    long long jac_off[AtLeastOne<gen::kNumJacBlocks>::value];
+    long long hess_off[AtLeastOne<gen::kNumHessBlocks>::value];
+};
+
+}  // namespace cfem

@@ -29,39 +29,12 @@
 #error "CFEM_TILE (threads per CTA == samples per tile) must be defined"
 #endif
 
+#include "cfem_args.cuh"
+
 namespace cfem {
 
 constexpr unsigned kF = 1u, kGrad = 2u, kG = 4u, kJac = 8u, kHess = 16u;
 constexpr int kWarpsPerCta = CFEM_TILE / 32;
-
-template <int N> struct AtLeastOne { static constexpr int value = N > 0 ? N : 1; };
-
-// Kernel argument block: everything is resolved on the host at cfem_create().
-struct KArgs {
-    long long N;            // samples per problem
-    long long ntiles;       // ceil(N / CFEM_TILE)
-    long long ndec, ncons, nnz_jac, nnz_hess;   // per-problem strides
-    int       nreduce;      // reduction slots per tile
-    double    obj_factor;
-    const double* dvec;
-    const double* lam;
-    const double* data[AtLeastOne<gen::kNumData>::value];
-    long long     data_rows[AtLeastOne<gen::kNumData>::value];
-    double        scalars[AtLeastOne<gen::kNumScalars>::value];
-    double* f;
-    double* grad;
-    double* g;
-    double* jac;
-    double* hess;
-    double* partials;       // [batch][ntiles][nreduce]
-    double* reduce;         // [batch][nreduce]
-    long long var_off[AtLeastOne<gen::kNumVars>::value];
-    long long var_rows[AtLeastOne<gen::kNumVars>::value];
-    long long cons_off[AtLeastOne<gen::kNumCons>::value];
-    long long fun_rows[AtLeastOne<gen::kNumFuns>::value];
-    long long jac_off[AtLeastOne<gen::kNumJacBlocks>::value];
-    long long hess_off[AtLeastOne<gen::kNumHessBlocks>::value];
-};
 
 // ---------------------------------------------------------------------------
 // staging
@@ -107,7 +80,7 @@ __device__ __forceinline__ void stage_rows(double* __restrict__ dst,
 // per-warp output transposition
 // ---------------------------------------------------------------------------
 
-constexpr int pad_odd(int c) { return c | 1; }
+__host__ __device__ constexpr int pad_odd(int c) { return c | 1; }
 
 // Lane parks its C values of one output block.
 template <int C>

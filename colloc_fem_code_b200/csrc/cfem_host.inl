@@ -31,6 +31,9 @@ struct cfem_problem {
     bool          have_lam = false;
     unsigned      valid = 0;
     cudaEvent_t   ev[16] = {};
+    cudaEvent_t   kev[2] = {};          // around the per-sample kernel
+    bool          timing = false;
+    bool          kev_valid = false;
     long long     launches = 0;
     void*         flush_buf = nullptr;
     size_t        flush_bytes = 0;
@@ -170,6 +173,7 @@ void cfem_destroy(cfem_problem* p)
     cudaFree(p->k.reduce);
     cudaFree(p->flush_buf);
     for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : p->kev) if (e) cudaEventDestroy(e);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -239,6 +243,7 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     CFEM_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     p->own_stream = true;
     for (cudaEvent_t& e : p->ev) CFEM_TRY(cudaEventCreate(&e));
+    for (cudaEvent_t& e : p->kev) CFEM_TRY(cudaEventCreate(&e));
     CFEM_TRY(cudaMalloc(&p->d_dvec, B * L.ndec * D));
     CFEM_TRY(cudaMalloc(&p->d_lam, B * (L.ncons > 0 ? L.ncons : 1) * D));
     CFEM_TRY(cudaMalloc(&k.f, B * D));
@@ -367,7 +372,12 @@ int cfem_eval(cfem_problem* p, uint32_t what)
     if (!mask) return cfem::fail(p, CFEM_EINVAL, "cfem_eval: no kernel for this selector", cudaSuccess);
     CFEM_CUDA(p, cudaSetDevice(p->device));
     const dim3 grid((unsigned)p->k.ntiles, (unsigned)p->batch);
+    if (p->timing) CFEM_CUDA(p, cudaEventRecord(p->kev[0], p->stream));
     CFEM_CUDA(p, gen::launch_sample(mask, grid, p->stream, p->k));
+    if (p->timing) {
+        CFEM_CUDA(p, cudaEventRecord(p->kev[1], p->stream));
+        p->kev_valid = true;
+    }
     p->launches += 1;
     if (gen::kNumParamEntries > 0 && (mask & (CFEM_G | CFEM_JAC | CFEM_HESS))) {
         CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->stream, p->k));
@@ -475,6 +485,25 @@ int cfem_event_elapsed_ms(cfem_problem* p, int32_t start_slot, int32_t stop_slot
     CFEM_CUDA(p, cudaSetDevice(p->device));
     CFEM_CUDA(p, cudaEventSynchronize(p->ev[stop_slot]));
     CFEM_CUDA(p, cudaEventElapsedTime(ms, p->ev[start_slot], p->ev[stop_slot]));
+    return CFEM_OK;
+}
+
+int cfem_set_kernel_timing(cfem_problem* p, int32_t enabled)
+{
+    if (!p) return CFEM_EINVAL;
+    p->timing = enabled != 0;
+    p->kev_valid = false;
+    return CFEM_OK;
+}
+
+int cfem_last_sample_kernel_ms(cfem_problem* p, float* ms)
+{
+    if (!p || !ms) return CFEM_EINVAL;
+    if (!p->kev_valid)
+        return cfem::fail(p, CFEM_ESTATE, "cfem_last_sample_kernel_ms: no timed launch", cudaSuccess);
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    CFEM_CUDA(p, cudaEventSynchronize(p->kev[1]));
+    CFEM_CUDA(p, cudaEventElapsedTime(ms, p->kev[0], p->kev[1]));
     return CFEM_OK;
 }
 

@@ -149,6 +149,11 @@ int          cfem_synchronize(cfem_problem* p);
 int          cfem_event_record(cfem_problem* p, int32_t slot);
 int          cfem_event_elapsed_ms(cfem_problem* p, int32_t start_slot,
                                    int32_t stop_slot, float* ms);
+/* When enabled, every cfem_eval brackets its per-sample kernel (the dominant,
+ * HBM-bound launch) with CUDA events on the handle's stream;
+ * cfem_last_sample_kernel_ms returns the duration of the latest such launch. */
+int          cfem_set_kernel_timing(cfem_problem* p, int32_t enabled);
+int          cfem_last_sample_kernel_ms(cfem_problem* p, float* ms);
 /* Number of kernels this handle has launched so far. */
 int64_t      cfem_launch_count(const cfem_problem* p);
 /* Write `bytes` of zeros to a scratch buffer (L2 flush between timed iterations). */

@@ -1,0 +1,194 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.
+
+Tolerances (FP64): 1e-12 relative, as BASELINE.json's north star states.  For
+constraint values, which are differences of O(1) terms that cancel at a
+solution, "relative" is relative to the magnitude of the terms
+(|value| + scale), not to the possibly tiny residual.
+"""
+
+import numpy as np
+import pytest
+
+from colloc_fem_code_b200 import backend, families, synthetic
+from oracle import ref_models
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+MASKS = (1, 3, 4, 8, 16, 5, 15, 31)
+
+
+def _scale(*arrays):
+    return max(1.0, *(float(np.max(np.abs(a))) for a in arrays if a.size))
+
+
+def check_against(res, ref, scale):
+    """res / ref: dicts with f, grad, g, jac, hess."""
+    np.testing.assert_allclose(res['f'], ref['f'], rtol=RTOL)
+    np.testing.assert_allclose(res['grad'], ref['grad'], rtol=RTOL,
+                               atol=1e-300)
+    np.testing.assert_allclose(res['g'], ref['g'], rtol=RTOL,
+                               atol=RTOL * scale)
+    np.testing.assert_allclose(res['jac'], ref['jac'], rtol=RTOL,
+                               atol=RTOL * scale)
+    np.testing.assert_allclose(res['hess'], ref['hess'], rtol=RTOL,
+                               atol=RTOL * scale)
+
+
+def cuda_callbacks(p, dvec, sigma, lam):
+    """The five callbacks, one C-ABI call each (the IPOPT call pattern)."""
+    return {'f': p.obj(dvec), 'grad': p.obj_grad(dvec), 'g': p.constr(dvec),
+            'jac': p.constr_jac_val(dvec),
+            'hess': p.lag_hess_val(dvec, sigma, lam)}
+
+
+def oracle_callbacks(o, dvec, sigma, lam):
+    return {'f': o.obj(dvec), 'grad': o.obj_grad(dvec), 'g': o.constr(dvec),
+            'jac': o.constr_jac_val(dvec),
+            'hess': o.lag_hess_val(dvec, sigma, lam)}
+
+
+def test_golden_fixtures(golden):
+    g = golden
+    nx, nu, ny = g['dims']
+    p = families.make_problem(g['kind'], g['y'], g['u'], nx, dt=g['dt'])
+    ref = {'f': g['f'], 'grad': g['grad'], 'g': g['g'], 'jac': g['jac_val'],
+           'hess': g['hess_val']}
+    scale = _scale(g['dvec'], g['y'], g['u']) ** 2 * (nx + nu + ny + 1)
+    check_against(cuda_callbacks(p, g['dvec'], g['obj_factor'], g['lam']),
+                  ref, scale)
+    # fused single pass
+    f, grad, gg, jac, hess = p.backend.eval_all(g['dvec'], g['obj_factor'],
+                                                g['lam'])
+    check_against({'f': f, 'grad': grad, 'g': gg, 'jac': jac, 'hess': hess},
+                  ref, scale)
+
+
+def test_every_kernel_variant(golden):
+    """Each instantiated mask produces the same bits as the full kernel."""
+    g = golden
+    if g['kind'] not in ('innovation', 'ml_balanced', 'ndisc_zoh'):
+        pytest.skip('variant sweep runs on three families')
+    nx, nu, ny = g['dims']
+    p = families.make_problem(g['kind'], g['y'], g['u'], nx, dt=g['dt'])
+    h = p.backend.handle
+    h.set_dvec(g['dvec'])
+    h.set_multipliers(g['obj_factor'], g['lam'])
+    h.eval(backend.ALL)
+    full = {b: h.fetch(b).copy() for b in (1, 2, 4, 8, 16)}
+    for mask in MASKS:
+        h.set_dvec(g['dvec'])      # invalidates cached results
+        h.eval(mask)
+        for b in (1, 2, 4, 8, 16):
+            if mask & b:
+                np.testing.assert_array_equal(h.fetch(b), full[b],
+                                              err_msg=f'mask {mask} bit {b}')
+
+
+CASES = [
+    ('innovation', (2, 1, 2), 2), ('innovation', (2, 1, 2), 3),
+    ('innovation', (2, 1, 2), 257), ('innovation', (2, 1, 2), 10000),
+    ('balanced', (2, 1, 2), 1000), ('ml', (2, 1, 2), 1000),
+    ('ml_zoh', (2, 1, 2), 300), ('ndisc_zoh', (2, 1, 2), 257),
+    ('innovation', (5, 3, 3), 257), ('balanced', (5, 3, 3), 250),
+    ('ml_balanced', (5, 3, 3), 250), ('innovation', (5, 3, 3), 10000),
+    ('innovation', (4, 2, 7), 2), ('innovation', (4, 2, 7), 129),
+    ('ndisc_zoh', (4, 2, 7), 601), ('innovation', (4, 2, 7), 10000),
+    ('innovation', (1, 1, 1), 33), ('innovation', (3, 2, 1), 4097),
+]
+
+
+@pytest.mark.parametrize('kind,dims,N', CASES,
+                         ids=[f'{k}-{d[0]}{d[1]}{d[2]}-N{n}'
+                              for k, d, n in CASES])
+def test_random_point_vs_oracle(kind, dims, N):
+    nx, nu, ny = dims
+    exp = synthetic.experiment(N + 17, N, nx, nu, ny)
+    p = families.make_problem(kind, exp['y'], exp['u'], nx, dt=0.05)
+    o = ref_models.make_problem(kind, exp['y'], exp['u'], nx, dt=0.05)
+    dvec, lam, _ = synthetic.evaluation_point(p, exp, seed=N)
+    sigma = 0.8
+    scale = _scale(dvec, exp['y'], exp['u']) ** 2 * (nx + nu + ny + 1)
+    check_against(cuda_callbacks(p, dvec, sigma, lam),
+                  oracle_callbacks(o, dvec, sigma, lam), scale)
+
+
+def test_known_answer_noise_free():
+    """True states of noise-free data with en = 0: all defects are 0 to
+    rounding and f = -N log det sRp (symfem.py:50-65)."""
+    nx, nu, ny, N = 4, 2, 3, 5000
+    exp = synthetic.experiment(3, N, nx, nu, ny, std_w=0.0, std_v=0.0)
+    p = families.make_problem('innovation', exp['y'], exp['u'], nx)
+    dvec = np.zeros(p.ndec)
+    var = p.variables(dvec)
+    for k in 'ABCD':
+        var[k][...] = exp[k]
+    var['x'][...] = exp['x']
+    diag = np.array([1.5, 0.7, 1.1])
+    var['sRp_tril'][families.models.tril_diag(ny)] = diag
+    g = p.constr(dvec)
+    assert np.max(np.abs(g)) <= 1e-12 * _scale(exp['x'], exp['y'])
+    np.testing.assert_allclose(p.obj(dvec), -N * np.log(diag).sum(),
+                               rtol=RTOL)
+    grad = p.obj_grad(dvec)
+    sl = p.decision['sRp_tril']
+    np.testing.assert_allclose(
+        grad[sl.offset:sl.offset + sl.size][families.models.tril_diag(ny)],
+        -N / diag, rtol=RTOL)
+
+
+@pytest.mark.parametrize('dims', [(2, 1, 2), (5, 3, 3)],
+                         ids=['attas212', 'blackbox533'])
+def test_full_size_million_samples(dims):
+    """BASELINE size N = 1e6: direct NumPy restatement of the per-sample
+    values, and size-independent properties of the derivative values: the
+    per-sample functions are bilinear, so central differences are exact,
+    J(x) v = (g(x+v) - g(x-v)) / 2 and H(lam) v = (J(x+v)' - J(x-v)') lam / 2,
+    and the Hessian is linear in (sigma, lambda)."""
+    import scipy.sparse as sp
+    nx, nu, ny = dims
+    N = 1_000_000
+    exp = synthetic.experiment(0, N, nx, nu, ny)
+    p = families.make_problem('innovation', exp['y'], exp['u'], nx)
+    dvec, lam, sigma = synthetic.evaluation_point(p, exp)
+    var = p.variables(dvec)
+    x, en, y, u = var['x'], var['en'], exp['y'], exp['u']
+    sRp = families.models.tril_mat(var['sRp_tril'])
+    dyn = x[1:] - (x[:-1] @ var['A'].T + u[:-1] @ var['B'].T
+                   + en[:-1] @ var['Ln'].T)
+    inn = y - (x @ var['C'].T + u @ var['D'].T + var['ybias']) - en @ sRp.T
+    f = -0.5 * np.sum(en ** 2) - N * np.log(np.diag(sRp)).sum()
+    g = p.constr(dvec)
+    scale = _scale(dvec, y, u) ** 2 * (nx + nu + ny + 1)
+    np.testing.assert_allclose(g[:dyn.size], dyn.ravel(), rtol=RTOL,
+                               atol=RTOL * scale)
+    np.testing.assert_allclose(g[dyn.size:], inn.ravel(), rtol=RTOL,
+                               atol=RTOL * scale)
+    np.testing.assert_allclose(p.obj(dvec), f, rtol=RTOL)
+    grad = p.obj_grad(dvec)
+    eo = p.decision['en'].offset
+    np.testing.assert_array_equal(grad[eo:eo + en.size], -en.ravel())
+
+    rng = np.random.default_rng(9)
+    v = rng.normal(size=p.ndec)
+    jr, jc = p.constr_jac_ind()
+    jac = p.constr_jac_val(dvec)
+    J = sp.csr_matrix((jac, (jr, jc)), shape=(p.ncons, p.ndec))
+    fd = 0.5 * (p.constr(dvec + v) - p.constr(dvec - v))
+    np.testing.assert_allclose(J @ v, fd, rtol=1e-11,
+                               atol=1e-11 * scale * _scale(v))
+    hr, hc = p.lag_hess_ind()
+    hess0 = p.lag_hess_val(dvec, 0.0, lam)       # constraint part only
+    H = sp.csr_matrix((hess0, (hr, hc)), shape=(p.ndec, p.ndec))
+    H = H + sp.tril(H, -1).T
+    Jp = sp.csr_matrix((p.constr_jac_val(dvec + v), (jr, jc)),
+                       shape=(p.ncons, p.ndec))
+    Jm = sp.csr_matrix((p.constr_jac_val(dvec - v), (jr, jc)),
+                       shape=(p.ncons, p.ndec))
+    fdh = 0.5 * ((Jp.T @ lam) - (Jm.T @ lam))
+    np.testing.assert_allclose(H @ v, fdh, rtol=1e-10,
+                               atol=1e-10 * scale * _scale(v))
+    # linearity in the multipliers
+    hess1 = p.lag_hess_val(dvec, sigma, lam)
+    hess2 = p.lag_hess_val(dvec, 2 * sigma, 2 * lam)
+    np.testing.assert_allclose(hess2, 2 * hess1, rtol=1e-15)
