@@ -1,0 +1,418 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: NLP callback evaluations per second.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A *step* is one full callback set at a new decision vector -- objective,
+gradient, constraints, constraint-Jacobian values and Lagrangian-Hessian values
+(IPOPT's eval_f + eval_grad_f + eval_g + eval_jac_g + eval_h), per-sample AND
+parameter-only functions -- of the ATTAS short-period maximum-likelihood
+problem ((nx, nu, ny) = (2, 1, 2), attas_sp_ml.py:79-87 of the reference) on a
+synthetic trajectory of N = 1e6 samples per GPU.  With more than one GPU the
+trajectory is N = 1e6 x n_gpus samples, split in time with a one-sample halo;
+the objective and the parameter block of the gradient are all-reduced with
+NCCL every step (weak scaling).
+
+``value``  callback sets per second with inputs resident in HBM (events around
+           every step on the launching stream, L2 flushed between steps);
+           one "set" is normalised to N = 1e6 samples.
+``e2e``    the same through the host API: decision vector and multipliers in
+           pinned host memory -> H2D -> kernels -> D2H of all five results.
+``roofline``      HBM roofline of the fused per-sample kernel.
+``cpu_baseline``  the CPU oracle (NumPy restatement of the reference's
+           evaluation) timed on this box, rank 0, N = 1 only.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+KIND = 'ml'
+DIMS = (2, 1, 2)
+N_PER_GPU = 1_000_000
+METRIC = 'nlp_callback_evals_per_s'
+UNIT = 'callback sets/s (f+grad+g+Jac+Hess, N=1e6 samples per set)'
+FLUSH_BYTES = 256 << 20
+
+
+def algorithmic_bytes_per_sample(nx, nu, ny):
+    """every input read once, every output written
+    once, per sample, for the per-sample functions."""
+    nty = ny * (ny + 1) // 2
+    jd = nx * (1 + 2 * nx + 2 * ny + nu)
+    ji = 2 * nty + 2 * ny * nx + ny * nu + ny
+    hd = nx * nx + nx * ny
+    hi = nty + ny * nx
+    ho = 2 * ny
+    return 8 * ((nx + 2 * ny + nu) + 2 * (nx + ny) + ny + jd + ji
+                + hd + hi + ho)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured'
+    except Exception:
+        return 6650.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.device),
+                 f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [],
+                    'note': 'nvidia-smi unavailable'}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap')
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+class CudaArray:
+    """Zero-copy torch view of a device buffer owned by a cfem handle."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {
+            'shape': (n,), 'typestr': '<f8', 'data': (int(ptr), False),
+            'version': 2}
+
+
+def run_reference(args):
+    """The reference's CPU evaluation (the NumPy oracle port: the reference's
+    own stack -- ceacoest / sym2num -- is not installable), same workload."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    from colloc_fem_code_b200 import families, synthetic
+    from oracle import ref_models
+    nx, nu, ny = DIMS
+    N = N_PER_GPU
+    exp = synthetic.experiment(0, N, nx, nu, ny)
+    o = ref_models.make_problem(KIND, exp['y'], exp['u'], nx)
+    p = families.make_problem(KIND, exp['y'], exp['u'], nx)
+    dvec, lam, sigma = synthetic.evaluation_point(p, exp)
+    o.constr_jac_ind()
+    o.lag_hess_ind()
+
+    def step(i):
+        d = dvec + 1e-9 * i
+        o.obj(d)
+        o.obj_grad(d)
+        o.constr(d)
+        o.constr_jac_val(d)
+        o.lag_hess_val(d, sigma, lam)
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    sample = f'full workload: N={N} samples per step, {args.steps} steps'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': workload_config(1),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': 1,
+                         'kind': 'port', 'sample': sample,
+                         'host_cores_available': os.cpu_count()},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+    }))
+
+
+def workload_config(world):
+    nx, nu, ny = DIMS
+    return {
+        'workload': ('attas_sp_ml: MaximumLikelihoodDT (nx,nu,ny)=(2,1,2), '
+                     f'synthetic trajectory, N={N_PER_GPU} samples per GPU'),
+        'family': KIND, 'dims': list(DIMS),
+        'n_samples_total': N_PER_GPU * world,
+        'parallelism': 'single GPU' if world == 1 else
+        f'time-sharded x{world}, 1-sample halo, NCCL allreduce of objective '
+        '+ parameter gradient',
+        'l2': f'flushed between timed steps ({FLUSH_BYTES >> 20} MiB memset, '
+              'outside the per-step events); working set per step '
+              f'{algorithmic_bytes_per_sample(nx, nu, ny) * N_PER_GPU / 1e6:.0f}'
+              ' MB > 126 MB L2',
+    }
+
+
+def cpu_baseline():
+    """Oracle timed on one host core on a bounded sample of the workload."""
+    from colloc_fem_code_b200 import families, synthetic
+    from oracle import ref_models
+    nx, nu, ny = DIMS
+    N = N_PER_GPU
+    exp = synthetic.experiment(0, N, nx, nu, ny)
+    o = ref_models.make_problem(KIND, exp['y'], exp['u'], nx)
+    p = families.make_problem(KIND, exp['y'], exp['u'], nx)
+    dvec, lam, sigma = synthetic.evaluation_point(p, exp)
+    times = []
+    for i in range(4):
+        t0 = time.perf_counter()
+        o.obj(dvec)
+        o.obj_grad(dvec)
+        o.constr(dvec)
+        o.constr_jac_val(dvec)
+        o.lag_hess_val(dvec, sigma, lam)
+        times.append(time.perf_counter() - t0)
+    best = min(times[1:])
+    return {'value': 1.0 / best, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+            'sample': f'full workload N={N}, best of 3 callback sets after '
+                      '1 warm-up (index arrays excluded)',
+            'seconds_per_set': best,
+            'host_cores_available': os.cpu_count()}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from colloc_fem_code_b200 import backend, families, sharding, synthetic
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device(
+            'cuda', local_rank))
+
+    nx, nu, ny = DIMS
+    N = N_PER_GPU * world
+    exp = synthetic.experiment(0, N, nx, nu, ny)
+    problem = families.make_problem(KIND, exp['y'], exp['u'], nx)
+    dvec, lam, sigma = synthetic.evaluation_point(problem, exp)
+    ev = sharding.ShardedEvaluator(problem, rank, world, device=local_rank)
+    h = ev.handle
+    # one explicit stream for the kernels, the events and the NCCL calls
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    h.set_stream(stream.cuda_stream)
+    h.set_kernel_timing(True)
+    ldvec = ev.shard.local_dvec(dvec)
+    llam = ev.shard.local_multipliers(lam)
+    del exp
+
+    # ---- device-resident inputs (torch only owns the memory) -----------------
+    d_dvec = torch.from_numpy(ldvec).cuda()
+    d_lam = torch.from_numpy(llam).cuda()
+    h.set_dvec_device(d_dvec.data_ptr())
+    h.set_multipliers_device(sigma, d_lam.data_ptr())
+    ptrs = h.device_ptrs()
+    red = torch.as_tensor(CudaArray(ptrs['reduce'], ev.n_reduce),
+                          device=f'cuda:{local_rank}')
+
+    def device_step():
+        h.set_dvec_device(d_dvec.data_ptr())      # "new x": invalidates
+        h.eval(backend.ALL)
+        if world > 1:
+            dist.all_reduce(red)
+            h.apply_reduced(ptrs['reduce'])
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for _ in range(args.warmup):
+        h.flush_l2(FLUSH_BYTES)
+        device_step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = h.launch_count
+    kernel_ms = []
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        h.flush_l2(FLUSH_BYTES)
+        starts[i].record()
+        device_step()
+        stops[i].record()
+        if (i & 7) == 7 or i == args.steps - 1:
+            kernel_ms.append(h.last_sample_kernel_ms())
+    sync_all()
+    wall = time.perf_counter() - t_wall
+    launches = h.launch_count - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64,
+                            device=f'cuda:{local_rank}')
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+
+    # ---- end to end through the host API (pinned host buffers) ---------------
+    host = backend.HostBuffers(h)
+    host.dvec[:] = ldvec
+    host.lam[:] = llam
+
+    def e2e_step(i):
+        host.dvec[0] = ldvec[0] + 1e-12 * i      # a new x every step
+        h.set_dvec(host.dvec)
+        h.set_multipliers(sigma, host.lam)
+        h.eval(backend.ALL)
+        if world > 1:
+            dist.all_reduce(red)
+            h.apply_reduced(ptrs['reduce'])
+        host.fetch_all()
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        e2e_step(i)
+    sync_all()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(2 + i)
+    e1.record()
+    sync_all()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64,
+                          device=f'cuda:{local_rank}')
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        sets = args.steps * world           # N=1e6-sample callback sets
+        value = sets / (total_ms * 1e-3)
+        balg = algorithmic_bytes_per_sample(nx, nu, ny)
+        kms = float(np.mean(kernel_ms))
+        peak, peak_kind = measured_peak()
+        achieved = balg * ev.shard.n_local / (kms * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': workload_config(world),
+            'samples_per_s': value * N_PER_GPU,
+            'gpu_launches': int(launches),
+            'wall_s_timed_region': wall,
+            'clocks': clocks,
+            'e2e': {
+                'value': e2e_steps * world / (e2e_ms * 1e-3), 'unit': UNIT,
+                'h2d_bytes_per_step': int(8 * (h.ndec + h.ncons)),
+                'd2h_bytes_per_step': int(8 * (1 + h.ndec + h.ncons
+                                               + h.nnz_jac + h.nnz_hess)),
+                'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
+                'note': 'pinned host dvec+lambda -> H2D -> fused kernels -> '
+                        'D2H of f, grad, g, Jacobian and Hessian values '
+                        '(per rank)'},
+            'roofline': {
+                'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+                'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': ncu_traffic(),
+                'kernel': 'cfem_sample_kernel_m31',
+                'kernel_ms': kms, 'algorithmic_bytes_per_sample': balg,
+                'samples_per_launch': ev.shard.n_local,
+                'peak_source': f'{peak_kind} (MEASURED_PEAKS.json hbm_gbs, '
+                               'burst copy)',
+                'frac_of_nominal_8TBs': achieved / 8000.0},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu
+    capture (profiles/), or None."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        with open(path) as fh:
+            return json.load(fh)['cfem_sample_kernel_m31']['dram_bytes']
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

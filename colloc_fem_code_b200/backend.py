@@ -67,6 +67,8 @@ ABI = {
     'cfem_eval': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32]),
     'cfem_fetch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32,
                                   ctypes.c_void_p]),
+    'cfem_fetch_async': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32,
+                                        ctypes.c_void_p]),
     'cfem_eval_f': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'cfem_eval_grad_f': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'cfem_eval_g': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
@@ -337,6 +339,12 @@ class Handle:
                                         out.ctypes.data))
         return out
 
+    def fetch_async(self, which, out):
+        """Enqueue the D2H copy of one result into ``out`` (pinned memory);
+        valid after :meth:`synchronize`."""
+        self._check(self.lib.cfem_fetch_async(self._ptr, int(which),
+                                              out.ctypes.data))
+
     def synchronize(self):
         self._check(self.lib.cfem_synchronize(self._ptr))
 
@@ -400,6 +408,36 @@ class PinnedArray:
             self.close()
         except Exception:
             pass
+
+
+class HostBuffers:
+    """Page-locked host staging for every input and result of a handle: the
+    buffers an NLP solver's callbacks read from / write to."""
+
+    _FIELDS = (('dvec', 'ndec'), ('lam', 'ncons'), ('grad', 'ndec'),
+               ('g', 'ncons'), ('jac', 'nnz_jac'), ('hess', 'nnz_hess'))
+
+    def __init__(self, handle):
+        self.handle = handle
+        self._pinned = {}
+        for name, size in self._FIELDS:
+            n = handle.batch * getattr(handle, size)
+            self._pinned[name] = PinnedArray(handle.lib, n)
+            setattr(self, name, self._pinned[name].array)
+        self._pinned['f'] = PinnedArray(handle.lib, handle.batch)
+        self.f = self._pinned['f'].array
+
+    def fetch_all(self):
+        h = self.handle
+        for bit, name in ((F, 'f'), (GRAD, 'grad'), (G, 'g'), (JAC, 'jac'),
+                          (HESS, 'hess')):
+            if getattr(self, name).size:
+                h.fetch_async(bit, getattr(self, name))
+        h.synchronize()
+
+    def close(self):
+        for p in self._pinned.values():
+            p.close()
 
 
 class ProblemBackend:

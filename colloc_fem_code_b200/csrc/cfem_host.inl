@@ -391,7 +391,7 @@ int cfem_eval(cfem_problem* p, uint32_t what)
     return CFEM_OK;
 }
 
-int cfem_fetch(cfem_problem* p, uint32_t which, double* host_out)
+int cfem_fetch_async(cfem_problem* p, uint32_t which, double* host_out)
 {
     if (!p || !host_out) return CFEM_EINVAL;
     const double* src = nullptr;
@@ -411,6 +411,13 @@ int cfem_fetch(cfem_problem* p, uint32_t which, double* host_out)
     if (n)
         CFEM_CUDA(p, cudaMemcpyAsync(host_out, src, n * sizeof(double),
                                      cudaMemcpyDeviceToHost, p->stream));
+    return CFEM_OK;
+}
+
+int cfem_fetch(cfem_problem* p, uint32_t which, double* host_out)
+{
+    int rc = cfem_fetch_async(p, which, host_out);
+    if (rc) return rc;
     CFEM_CUDA(p, cudaStreamSynchronize(p->stream));
     return CFEM_OK;
 }

@@ -125,6 +125,9 @@ int          cfem_set_multipliers_device(cfem_problem* p, double obj_factor,
 int          cfem_eval(cfem_problem* p, uint32_t what);
 /* Copy ONE result (a single CFEM_* bit) to host memory and synchronise. */
 int          cfem_fetch(cfem_problem* p, uint32_t which, double* host_out);
+/* Same copy without the synchronisation (host_out should be pinned memory);
+ * complete after cfem_synchronize(). */
+int          cfem_fetch_async(cfem_problem* p, uint32_t which, double* host_out);
 /* IPOPT-shaped conveniences: evaluate if stale, copy to host, synchronise. */
 int          cfem_eval_f(cfem_problem* p, double* f);
 int          cfem_eval_grad_f(cfem_problem* p, double* grad);
