@@ -137,7 +137,8 @@ def _nvcc(args, what):
     return proc.stderr
 
 
-def build_library(structure, label='model', verbose=False, **gen_kwargs):
+def build_library(structure, label='model', verbose=False, files=None,
+                  **gen_kwargs):
     """Generate + compile the library of ``structure``; returns the .so path.
 
     Two translation units (``codegen.Generator.sources``) are compiled to
@@ -153,6 +154,11 @@ def build_library(structure, label='model', verbose=False, **gen_kwargs):
                        _read(os.path.join(CSRC, 'cfem_host.inl')),
                        _read(os.path.join(INCLUDE, 'cfem.h')))
     so_path = os.path.join(GEN_DIR, f'cfem_{label}_{key_main}{key_param}.so')
+    if files is not None:       # every artefact this library is made of
+        files.append(so_path)
+        for unit, key in (('param', key_param), ('main', key_main)):
+            stem = os.path.join(GEN_DIR, f'cfem_{label}_{unit}_{key}')
+            files += [stem + '.o', stem + '.cu']
     if os.path.isfile(so_path):
         return so_path
     with _build_lock:

@@ -19,8 +19,9 @@ Kernels per library
       one staging of the tile's inputs;
   cfem_param_kernel           one thread per entry of the parameter-only
       functions (values, Jacobian, Hessian);
-  cfem_finalize_kernel        fixed-order reduction over tiles + the
-      sample-independent objective terms (times the row count);
+  (finalisation)              the last CTA of a problem to retire does the
+      fixed-order reduction over tiles + the sample-independent objective
+      terms (times the row count) inside the per-sample kernel itself;
   cfem_apply_reduced_kernel   writes an externally all-reduced objective /
       parameter-gradient vector back (time-sharded multi-GPU runs).
 """
@@ -53,7 +54,8 @@ class _Item:
 
 
 class Generator:
-    def __init__(self, structure, tile=None, pass_budget=None, masks=None):
+    def __init__(self, structure, tile=None, pass_budget=None, masks=None,
+                 min_blocks=None):
         self.st = structure
         self.masks = tuple(masks or DEFAULT_MASKS)
         self.funs = structure.funs
@@ -67,12 +69,14 @@ class Generator:
                   if not self.funs[i]['is_objective'])
         if tile is None:
             tile = int(os.environ.get('CFEM_TILE', 0)) or \
-                (256 if inputs <= 16 else 128)
+                (64 if inputs <= 16 else 128)
         if pass_budget is None:
-            pass_budget = int(os.environ.get('CFEM_PASS_BUDGET', 0)) or 24
+            pass_budget = int(os.environ.get('CFEM_PASS_BUDGET', 0)) or 6
         assert tile % 32 == 0 and 32 <= tile <= 1024
         self.tile = tile
         self.pass_budget = pass_budget
+        self.min_blocks = min_blocks or int(
+            os.environ.get('CFEM_MIN_BLOCKS', 0))
         self._reduce_slots()
 
     # ------------------------------------------------------------------
@@ -300,7 +304,8 @@ class Generator:
             n for n, bit in (('F', F), ('GRAD', GRAD), ('G', G), ('JAC', JAC),
                              ('HESS', HESS)) if mask & bit))
         w.append(f'constexpr size_t kSmemBytes_m{mask} = {lay["total"] * 8};')
-        w.append(f'__global__ void __launch_bounds__({T})')
+        bounds = f'{T}, {self.min_blocks}' if self.min_blocks else f'{T}'
+        w.append(f'__global__ void __launch_bounds__({bounds})')
         w.append(f'cfem_sample_kernel_m{mask}(const cfem::KArgs a)')
         w.append('{')
         w.append('    extern __shared__ __align__(16) double smem[];')
@@ -396,9 +401,19 @@ class Generator:
             w.append('        }')
             w.append('    }')
         if mask & (F | GRAD):
+            if not nred:
+                w.append('    double red[1] = {0.0};')
             w.append(f'    cfem::block_reduce_store<{max(nred, 1)}>(red, smem + '
                      f'{lay["red_off"]}, a.partials + ((b * a.ntiles + '
                      f'blockIdx.x) * {max(nred, 1)}), tid);')
+            w.append('    // the last CTA of this problem to retire finalises '
+                     '(fixed summation order => deterministic)')
+            w.append(f'    if (cfem::last_block_done(a.done_count + b, '
+                     f'gridDim.x, tid)) {{')
+            w.append(f'        cfem_finalize(a, {mask}u, b, tid, smem + '
+                     f'{lay["red_off"]});')
+            w.append('        if (tid == 0) a.done_count[b] = 0u;')
+            w.append('    }')
         w.append('}')
         return '\n'.join(w), lay['total'] * 8
 
@@ -491,18 +506,17 @@ class Generator:
         R = len(self.slots)
         nd = max(1, len(self.dyn_slots))
         w = []
-        w.append('__global__ void __launch_bounds__(256)')
-        w.append('cfem_finalize_kernel(const cfem::KArgs a, const unsigned mask)')
+        w.append('// Runs in the last CTA of a problem (all CFEM_TILE threads).')
+        w.append('static __device__ __noinline__ void cfem_finalize('
+                 'const cfem::KArgs& a, const unsigned mask, const long long b, '
+                 'const int tid, double* scratch)')
         w.append('{')
-        w.append('    __shared__ double scratch[8];')
-        w.append('    const int tid = threadIdx.x;')
-        w.append('    const long long b = blockIdx.x;')
         w.append('    const double* __restrict__ dvec = a.dvec + b * a.ndec;')
         w.append(f'    const double* part = a.partials + b * a.ntiles * {nd};')
         w.append(f'    double tot[{R}];')
         w.append(f'    for (int r = 0; r < {R}; ++r) tot[r] = 0.0;')
         for di, slot in enumerate(self.dyn_slots):
-            w.append(f'    tot[{slot}] = cfem::reduce_tiles<256>(part, '
+            w.append(f'    tot[{slot}] = cfem::reduce_tiles<CFEM_TILE>(part, '
                      f'a.ntiles, {nd}, {di}, scratch, tid);')
         w.append('    if (tid != 0) return;')
         for fi, f in enumerate(self.funs):
@@ -676,8 +690,8 @@ class Generator:
         w.append('}  // namespace gen')
         w.append('#include "cfem_device.cuh"')
         w.append('namespace gen {')
-        w += kernels
         w.append(finalize)
+        w += kernels
         w.append(f'constexpr int kNumParamEntries = {self.n_param_entries};')
         w.append(launch_param_sig + ';    // parameter-only unit')
         w.append('static cudaError_t configure_kernels()')
@@ -700,12 +714,6 @@ class Generator:
                      f'kSmemBytes_m{m}, s>>>(a); break;')
         w.append('    default: return cudaErrorInvalidValue;')
         w.append('    }')
-        w.append('    return cudaGetLastError();')
-        w.append('}')
-        w.append('static cudaError_t launch_finalize(unsigned mask, int batch, '
-                 'cudaStream_t s, const cfem::KArgs& a)')
-        w.append('{')
-        w.append('    cfem_finalize_kernel<<<batch, 256, 0, s>>>(a, mask);')
         w.append('    return cudaGetLastError();')
         w.append('}')
         w.append('static cudaError_t launch_apply_reduced(int batch, '

@@ -27,6 +27,7 @@ struct KArgs {
     double* jac;
     double* hess;
     double* partials;       // [batch][ntiles][nreduce]
+    unsigned int* done_count;   // [batch] retired-CTA counters (zero between launches)
     double* reduce;         // [batch][nreduce]
     long long var_off[AtLeastOne<gen::kNumVars>::value];
     long long var_rows[AtLeastOne<gen::kNumVars>::value];

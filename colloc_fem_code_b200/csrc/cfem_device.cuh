@@ -148,7 +148,21 @@ __device__ __forceinline__ void block_reduce_store(const double (&v)[R],
 #pragma unroll
         for (int w = 0; w < kWarpsPerCta; ++w) s += scratch[w * R + tid];
         out[tid] = s;
+        __threadfence();        // publish before the retirement counter moves
     }
+}
+
+// "Last block done" hand-shake: every CTA of a problem bumps the problem's
+// counter once its partial sums are globally visible; the CTA that observes
+// count == nblocks - 1 is the last one and returns true (in all its threads).
+__device__ __forceinline__ bool last_block_done(unsigned int* counter,
+                                                unsigned int nblocks, int tid)
+{
+    __shared__ unsigned int s_last;
+    __syncthreads();            // the writers' fences are behind us
+    if (tid == 0) s_last = (atomicAdd(counter, 1u) == nblocks - 1u) ? 1u : 0u;
+    __syncthreads();
+    return s_last != 0u;
 }
 
 // Fixed-order sum over tiles of one reduction slot (one CTA per problem).
@@ -160,7 +174,7 @@ __device__ __forceinline__ double reduce_tiles(const double* __restrict__ part,
 {
     double s = 0.0;
     for (long long t = tid; t < ntiles; t += THREADS)
-        s += part[t * nreduce + slot];
+        s += __ldcg(part + t * nreduce + slot);     // written by other SMs
     s = warp_sum(s);
     __syncthreads();
     if ((tid & 31) == 0) scratch[tid >> 5] = s;

@@ -20,6 +20,8 @@ struct cfem_problem {
     int           device = 0;
     cudaStream_t  stream = nullptr;
     bool          own_stream = false;
+    cudaStream_t  aux_stream = nullptr;     // parameter-only kernel, concurrent
+    cudaEvent_t   ev_fork = nullptr, ev_join = nullptr;
     long long     N = 0;
     int           batch = 1;
     int           halo = 0;
@@ -170,6 +172,10 @@ void cfem_destroy(cfem_problem* p)
     cudaFree(p->k.jac);
     cudaFree(p->k.hess);
     cudaFree(p->k.partials);
+    cudaFree(p->k.done_count);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
+    if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
     cudaFree(p->k.reduce);
     cudaFree(p->flush_buf);
     for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
@@ -242,6 +248,9 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     const size_t B = (size_t)batch, D = sizeof(double);
     CFEM_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     p->own_stream = true;
+    CFEM_TRY(cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking));
+    CFEM_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    CFEM_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     for (cudaEvent_t& e : p->ev) CFEM_TRY(cudaEventCreate(&e));
     for (cudaEvent_t& e : p->kev) CFEM_TRY(cudaEventCreate(&e));
     CFEM_TRY(cudaMalloc(&p->d_dvec, B * L.ndec * D));
@@ -253,6 +262,8 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     CFEM_TRY(cudaMalloc(&k.hess, B * (L.nnz_hess > 0 ? L.nnz_hess : 1) * D));
     CFEM_TRY(cudaMalloc(&k.partials, B * k.ntiles * gen::kNumDynReduce * D));
     CFEM_TRY(cudaMalloc(&k.reduce, B * gen::kNumReduce * D));
+    CFEM_TRY(cudaMalloc(&k.done_count, B * sizeof(unsigned int)));
+    CFEM_TRY(cudaMemset(k.done_count, 0, B * sizeof(unsigned int)));
     // structurally-zero gradient entries are written once, here
     CFEM_TRY(cudaMemset(k.grad, 0, B * L.ndec * D));
     CFEM_TRY(cudaMemset(k.reduce, 0, B * gen::kNumReduce * D));
@@ -372,6 +383,17 @@ int cfem_eval(cfem_problem* p, uint32_t what)
     if (!mask) return cfem::fail(p, CFEM_EINVAL, "cfem_eval: no kernel for this selector", cudaSuccess);
     CFEM_CUDA(p, cudaSetDevice(p->device));
     const dim3 grid((unsigned)p->k.ntiles, (unsigned)p->batch);
+    // The parameter-only functions are independent of the per-sample pass:
+    // fork them onto the auxiliary stream so that they overlap it.
+    const bool params = gen::kNumParamEntries > 0 &&
+                        (mask & (CFEM_G | CFEM_JAC | CFEM_HESS));
+    if (params) {
+        CFEM_CUDA(p, cudaEventRecord(p->ev_fork, p->stream));
+        CFEM_CUDA(p, cudaStreamWaitEvent(p->aux_stream, p->ev_fork, 0));
+        CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->aux_stream, p->k));
+        CFEM_CUDA(p, cudaEventRecord(p->ev_join, p->aux_stream));
+        p->launches += 1;
+    }
     if (p->timing) CFEM_CUDA(p, cudaEventRecord(p->kev[0], p->stream));
     CFEM_CUDA(p, gen::launch_sample(mask, grid, p->stream, p->k));
     if (p->timing) {
@@ -379,14 +401,7 @@ int cfem_eval(cfem_problem* p, uint32_t what)
         p->kev_valid = true;
     }
     p->launches += 1;
-    if (gen::kNumParamEntries > 0 && (mask & (CFEM_G | CFEM_JAC | CFEM_HESS))) {
-        CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->stream, p->k));
-        p->launches += 1;
-    }
-    if (mask & (CFEM_F | CFEM_GRAD)) {
-        CFEM_CUDA(p, gen::launch_finalize(mask, p->batch, p->stream, p->k));
-        p->launches += 1;
-    }
+    if (params) CFEM_CUDA(p, cudaStreamWaitEvent(p->stream, p->ev_join, 0));
     p->valid |= mask;
     return CFEM_OK;
 }

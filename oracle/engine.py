@@ -257,7 +257,7 @@ class _Registered:
         Returns an ``[M, core]`` integer array; parameters broadcast over M.
         """
         p = self.problem
-        spec = p.decision.get(arg) or p.dependent[arg]
+        spec = p.dependent.get(arg) or p.decision[arg]
         core = int(np.prod(self.fun.arg_syms[arg].shape, dtype=np.int64))
         ind = spec.offset + np.arange(spec.size, dtype=np.int64)
         ind = ind.reshape(-1, core)

@@ -278,15 +278,20 @@ class FilterErrorModel(engine.Model):
 class FilterErrorProblem(engine.Problem):
     """All problem families of fem.py, switched on by ``features``."""
 
-    def __init__(self, model, y, u, features=()):
+    def __init__(self, model, y, u, features=(), halo=0):
+        """``halo=1`` states the left/inner shard of a time-split trajectory
+        (no reference counterpart; used by the multi-process tests): ``x``
+        carries one extra row owned by the right neighbour and ``dynamics``
+        has N rows instead of N-1."""
         super().__init__()
         self.model = model
         self.features = tuple(features)
         self.y = np.asarray(y, dtype=float)
         self.u = np.asarray(u, dtype=float)
-        self.uprev = self.u[:-1]
         N = len(self.y)
         self.N = N
+        M = N - 1 + halo            # rows of the one-step functions
+        self.uprev = self.u[:M]
         nx, nu, ny = model.nx, model.nu, model.ny
         assert self.y.shape == (N, ny) and self.u.shape == (N, nu) and N > 1
 
@@ -295,16 +300,19 @@ class FilterErrorProblem(engine.Problem):
                             ('A', (nx, nx)), ('B', (nx, nu)), ('C', (ny, nx)),
                             ('D', (ny, nu)), ('Ln', (nx, ny))):
             self.add_decision(name, shape)
-        x = self.add_decision('x', (N, nx))
+        x = self.add_decision('x', (N + halo, nx))
         en = self.add_decision('en', (N, ny))
         # fem.py:47-52
         D = engine.Decision
-        self.add_dependent_variable('xprev', D((N - 1, nx), x.offset))
-        self.add_dependent_variable('enprev', D((N - 1, ny), en.offset))
-        self.add_dependent_variable('xnext', D((N - 1, nx), x.offset + nx))
+        self.add_dependent_variable('xprev', D((M, nx), x.offset))
+        self.add_dependent_variable('enprev', D((M, ny), en.offset))
+        self.add_dependent_variable('xnext', D((M, nx), x.offset + nx))
+        if halo:
+            # the per-sample functions of this shard see its own N rows of x
+            self.add_dependent_variable('x', D((N, nx), x.offset))
         # fem.py:55-57
         self.add_objective(model.loglikelihood, N)
-        self.add_constraint(model.dynamics, (N - 1, nx))
+        self.add_constraint(model.dynamics, (M, nx))
         self.add_constraint(model.innovation, (N, ny))
 
         for feat in self.features:
@@ -376,10 +384,10 @@ def make_model(kind, nx, nu, ny):
     return _model_cache[key]()
 
 
-def make_problem(kind, y, u, nx, dt=None):
+def make_problem(kind, y, u, nx, dt=None, halo=0):
     y = np.asarray(y, dtype=float)
     u = np.asarray(u, dtype=float)
     model = make_model(kind, nx, u.shape[1], y.shape[1])
     if dt is not None:
         model.dt = dt
-    return FilterErrorProblem(model, y, u, KINDS[kind])
+    return FilterErrorProblem(model, y, u, KINDS[kind], halo=halo)

@@ -1,0 +1,87 @@
+#!/usr/bin/env python3
+"""Kernel tuning sweep: build variants of one model library (tile size, output
+pass budget, ...) and time the fused per-sample kernel on the GPU.
+
+    python tools/sweep.py build   # here (no GPU): compile every variant
+    python tools/sweep.py run     # on the GPU box: time them
+"""
+import itertools
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from colloc_fem_code_b200 import backend, families, synthetic  # noqa: E402
+
+KIND = os.environ.get('SWEEP_KIND', 'ml')
+DIMS = tuple(int(c) for c in os.environ.get('SWEEP_DIMS', '212'))
+N = int(os.environ.get('SWEEP_N', 1_000_000))
+VARIANTS = []
+for t, b in itertools.product((32, 64, 128), (4, 8)):
+    for warps in (0, 48, 64):       # resident warps per SM asked of ptxas
+        mb = min(32, warps * 32 // t)
+        v = dict(tile=t, pass_budget=b, min_blocks=mb)
+        if v not in VARIANTS:
+            VARIANTS.append(v)
+
+
+def problem():
+    nx, nu, ny = DIMS
+    exp = synthetic.experiment(0, N, nx, nu, ny)
+    p = families.make_problem(KIND, exp['y'], exp['u'], nx, dt=0.05)
+    return exp, p
+
+
+def build():
+    import concurrent.futures as cf
+    nx, nu, ny = DIMS
+    p = families.make_problem(KIND, np.zeros((4, ny)), np.zeros((4, nu)), nx,
+                              dt=0.05)
+    st = p.structure
+    with cf.ThreadPoolExecutor(8) as pool:
+        futs = [pool.submit(backend.build_library, st,
+                            backend.structure_label(st), masks=(31,), **v)
+                for v in VARIANTS]
+        for v, f in zip(VARIANTS, futs):
+            print(v, os.path.basename(f.result()))
+
+
+def run():
+    nx, nu, ny = DIMS
+    exp, p = problem()
+    st = p.structure
+    dvec, lam, sigma = synthetic.evaluation_point(p, exp)
+    balg = 0
+    sys.path.insert(0, ROOT)
+    import bench
+    balg = bench.algorithmic_bytes_per_sample(nx, nu, ny)
+    out = []
+    for v in VARIANTS:
+        lib = backend.Library.load(backend.build_library(
+            st, backend.structure_label(st), masks=(31,), **v))
+        h = backend.Handle(lib, st.N, [d['source'] for d in st.data],
+                           st.scalar_values)
+        h.set_kernel_timing(True)
+        h.set_dvec(dvec)
+        h.set_multipliers(sigma, lam)
+        ms = []
+        for i in range(13):
+            h.flush_l2(256 << 20)
+            h.set_dvec_device(h.device_ptrs()['dvec'])
+            h.eval(31)
+            ms.append(h.last_sample_kernel_ms())
+        ms = ms[3:]
+        rec = dict(v, ms_min=min(ms), ms_med=float(np.median(ms)),
+                   gbs=balg * N / (np.median(ms) * 1e-3) / 1e9)
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
+        h.close()
+    return out
+
+
+if __name__ == '__main__':
+    {'build': build, 'run': run}[sys.argv[1]]()
