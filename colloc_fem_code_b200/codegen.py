@@ -306,7 +306,7 @@ class Generator:
         w.append(f'constexpr size_t kSmemBytes_m{mask} = {lay["total"] * 8};')
         bounds = f'{T}, {self.min_blocks}' if self.min_blocks else f'{T}'
         w.append(f'__global__ void __launch_bounds__({bounds})')
-        w.append(f'cfem_sample_kernel_m{mask}(const cfem::KArgs a)')
+        w.append(f'cfem_sample_kernel_m{mask}(const __grid_constant__ cfem::KArgs a)')
         w.append('{')
         w.append('    extern __shared__ __align__(16) double smem[];')
         w.append('    const int tid = threadIdx.x, lane = tid & 31, '
