@@ -172,9 +172,18 @@ __device__ __forceinline__ double reduce_tiles(const double* __restrict__ part,
                                                int slot, double* scratch,
                                                int tid)
 {
-    double s = 0.0;
-    for (long long t = tid; t < ntiles; t += THREADS)
-        s += __ldcg(part + t * nreduce + slot);     // written by other SMs
+    // 8 independent accumulators keep 8 L2 loads in flight per thread; the
+    // association order is fixed, so the sum is reproducible run to run.
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    long long t = tid;
+    for (; t + 7 * THREADS < ntiles; t += 8 * THREADS) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)     // partials were written by other SMs
+            acc[u] += __ldcg(part + (t + (long long)u * THREADS) * nreduce + slot);
+    }
+    for (; t < ntiles; t += THREADS) acc[0] += __ldcg(part + t * nreduce + slot);
+    double s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) +
+               ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     s = warp_sum(s);
     __syncthreads();
     if ((tid & 31) == 0) scratch[tid >> 5] = s;
