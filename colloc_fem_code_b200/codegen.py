@@ -403,13 +403,10 @@ class Generator:
         if mask & (F | GRAD):
             if not nred:
                 w.append('    double red[1] = {0.0};')
-            w.append(f'    cfem::block_reduce_store<{max(nred, 1)}>(red, smem + '
-                     f'{lay["red_off"]}, a.partials + ((b * a.ntiles + '
-                     f'blockIdx.x) * {max(nred, 1)}), tid);')
-            w.append('    // the last CTA of this problem to retire finalises '
-                     '(fixed summation order => deterministic)')
-            w.append(f'    if (cfem::last_block_done(a.done_count + b, '
-                     f'gridDim.x, tid)) {{')
+            w.append(f'    if (cfem::tree_reduce<{max(nred, 1)}>(a, b, red, smem + '
+                     f'{lay["red_off"]}, tid)) {{')
+            w.append('        // this CTA retired last: it finalises (fixed '
+                     'summation tree => deterministic)')
             w.append(f'        cfem_finalize(a, {mask}u, b, tid, smem + '
                      f'{lay["red_off"]});')
             w.append('        if (tid == 0) a.done_count[b] = 0u;')
@@ -512,12 +509,12 @@ class Generator:
                  'const int tid, double* scratch)')
         w.append('{')
         w.append('    const double* __restrict__ dvec = a.dvec + b * a.ndec;')
-        w.append(f'    const double* part = a.partials + b * a.ntiles * {nd};')
+        w.append(f'    const double* part = a.gpartials + b * a.ngroups * {nd};')
         w.append(f'    double tot[{R}];')
         w.append(f'    for (int r = 0; r < {R}; ++r) tot[r] = 0.0;')
         for di, slot in enumerate(self.dyn_slots):
             w.append(f'    tot[{slot}] = cfem::reduce_tiles<CFEM_TILE>(part, '
-                     f'a.ntiles, {nd}, {di}, scratch, tid);')
+                     f'a.ngroups, {nd}, {di}, scratch, tid);')
         w.append('    if (tid != 0) return;')
         for fi, f in enumerate(self.funs):
             if not f['is_objective']:

@@ -27,7 +27,11 @@ struct KArgs {
     double* jac;
     double* hess;
     double* partials;       // [batch][ntiles][nreduce]
-    unsigned int* done_count;   // [batch] retired-CTA counters (zero between launches)
+    // two-level deterministic reduction tree (all counters zero between launches)
+    long long     ngroups;      // ceil(ntiles / kReduceGroup)
+    double*       gpartials;    // [batch][ngroups][nreduce]
+    unsigned int* group_count;  // [batch][ngroups] CTAs retired per group
+    unsigned int* done_count;   // [batch] groups retired per problem
     double* reduce;         // [batch][nreduce]
     long long var_off[AtLeastOne<gen::kNumVars>::value];
     long long var_rows[AtLeastOne<gen::kNumVars>::value];

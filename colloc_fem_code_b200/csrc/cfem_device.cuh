@@ -35,6 +35,7 @@ namespace cfem {
 
 constexpr unsigned kF = 1u, kGrad = 2u, kG = 4u, kJac = 8u, kHess = 16u;
 constexpr int kWarpsPerCta = CFEM_TILE / 32;
+constexpr int kReduceGroup = 256;       // CTAs per first-level reduction group
 
 // ---------------------------------------------------------------------------
 // staging
@@ -194,6 +195,43 @@ __device__ __forceinline__ double reduce_tiles(const double* __restrict__ part,
         for (int w = 0; w < THREADS / 32; ++w) tot += scratch[w];
     }
     return tot;     // valid in thread 0
+}
+
+// Two-level reduction of the per-thread partial sums `v` of every CTA of
+// problem `b` (objective and parameter-gradient terms):
+//   level 0  CTA tree (warp shuffles + shared memory) -> partials[tile]
+//   level 1  the last CTA of every group of kReduceGroup tiles to retire sums
+//            the group's partials in tile order       -> gpartials[group]
+//   level 2  the last group to retire returns true: its CTA sums gpartials in
+//            group order (cfem_finalize in the generated code).
+// No floating-point atomics and a fixed association order: bitwise
+// reproducible run to run, independent of CTA scheduling; the serial tail is
+// two short rounds of L2 loads however long the trajectory is.
+template <int R>
+__device__ __forceinline__ bool tree_reduce(const KArgs& a, long long b,
+                                            const double (&v)[R],
+                                            double* __restrict__ scratch,
+                                            int tid)
+{
+    const long long tile = blockIdx.x;
+    block_reduce_store<R>(v, scratch, a.partials + (b * a.ntiles + tile) * R, tid);
+    const long long g = tile / kReduceGroup;
+    const long long first = g * kReduceGroup;
+    const long long left = a.ntiles - first;
+    const unsigned in_group = left < kReduceGroup ? (unsigned)left : (unsigned)kReduceGroup;
+    unsigned int* gcount = a.group_count + b * a.ngroups + g;
+    if (!last_block_done(gcount, in_group, tid)) return false;
+    const double* part = a.partials + (b * a.ntiles + first) * R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double s = reduce_tiles<CFEM_TILE>(part, in_group, R, r, scratch, tid);
+        if (tid == 0) a.gpartials[(b * a.ngroups + g) * R + r] = s;
+    }
+    if (tid == 0) {
+        *gcount = 0u;
+        __threadfence();
+    }
+    return last_block_done(a.done_count + b, (unsigned)a.ngroups, tid);
 }
 
 }  // namespace cfem

@@ -173,6 +173,8 @@ void cfem_destroy(cfem_problem* p)
     cudaFree(p->k.hess);
     cudaFree(p->k.partials);
     cudaFree(p->k.done_count);
+    cudaFree(p->k.group_count);
+    cudaFree(p->k.gpartials);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
@@ -222,6 +224,7 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     memset(&k, 0, sizeof k);
     k.N = n_samples;
     k.ntiles = (n_samples + CFEM_TILE - 1) / CFEM_TILE;
+    k.ngroups = (k.ntiles + cfem::kReduceGroup - 1) / cfem::kReduceGroup;
     k.ndec = L.ndec; k.ncons = L.ncons; k.nnz_jac = L.nnz_jac; k.nnz_hess = L.nnz_hess;
     k.nreduce = gen::kNumReduce;
     k.obj_factor = 1.0;
@@ -262,6 +265,9 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     CFEM_TRY(cudaMalloc(&k.hess, B * (L.nnz_hess > 0 ? L.nnz_hess : 1) * D));
     CFEM_TRY(cudaMalloc(&k.partials, B * k.ntiles * gen::kNumDynReduce * D));
     CFEM_TRY(cudaMalloc(&k.reduce, B * gen::kNumReduce * D));
+    CFEM_TRY(cudaMalloc(&k.gpartials, B * k.ngroups * gen::kNumDynReduce * D));
+    CFEM_TRY(cudaMalloc(&k.group_count, B * k.ngroups * sizeof(unsigned int)));
+    CFEM_TRY(cudaMemset(k.group_count, 0, B * k.ngroups * sizeof(unsigned int)));
     CFEM_TRY(cudaMalloc(&k.done_count, B * sizeof(unsigned int)));
     CFEM_TRY(cudaMemset(k.done_count, 0, B * sizeof(unsigned int)));
     // structurally-zero gradient entries are written once, here
