@@ -39,8 +39,13 @@ ALL = 31
 DEFAULT_MASKS = (F, F | GRAD, G, JAC, HESS, F | G, F | GRAD | G | JAC, ALL)
 
 
-def _pad_odd(c):
-    return c | 1
+def _skew_size(c, rows):
+    """Doubles of a [rows][c] array in the Skew<c> layout of cfem_device.cuh,
+    rounded up to an even count (16-byte alignment of what follows)."""
+    import math
+    m = 16 // math.gcd(c, 16)
+    n = rows * c + (rows + m - 1) // m
+    return n + (n & 1)
 
 
 class _Item:
@@ -142,7 +147,7 @@ class Generator:
                 st = layout['stor'][key]
                 lines.append(
                     f'const double {ident} = {st["name"]}'
-                    f'[(tid + {ref[2]}) * {st["pad"]} + {flat}];')
+                    f'[cfem::Skew<{st["core"]}>::row(tid + {ref[2]}) + {flat}];')
         return lines, undefs
 
     # ------------------------------------------------------------------
@@ -258,18 +263,17 @@ class Generator:
             else:
                 core = self.funs[key[1]]['out_core']
             s['core'] = core
-            s['pad'] = core if core == 1 else _pad_odd(core)
             s['nrows'] = self.tile + s['shift']
             s['name'] = f's_{key[0]}{key[1]}'
             off += off & 1      # keep 16-byte alignment of every region
             s['off'] = off
-            off += s['nrows'] * s['pad']
+            off += _skew_size(core, s['nrows'])
         # output passes: group the items of every function under the budget
         wbuf = 0
         for p in plan:
             passes, cur, used = [], [], 0
             for it in p['items']:
-                need = 0 if it.c == 1 else _pad_odd(it.c)
+                need = 0 if it.c == 1 else it.c + 1
                 if cur and used + need > self.pass_budget:
                     passes.append(cur)
                     cur, used = [], 0
@@ -279,7 +283,7 @@ class Generator:
                 passes.append(cur)
             p['passes'] = passes
             for ps in passes:
-                wbuf = max(wbuf, sum(0 if it.c == 1 else 32 * _pad_odd(it.c)
+                wbuf = max(wbuf, sum(0 if it.c == 1 else _skew_size(it.c, 32)
                                      for it in ps))
         warps = self.tile // 32
         off += off & 1
@@ -339,7 +343,7 @@ class Generator:
                 ci = self.funs[key[1]]['cons_index']
                 src = f'a.lam + b * a.ncons + a.cons_off[{ci}]'
                 rows = f'a.fun_rows[{key[1]}]'
-            w.append(f'    cfem::stage_rows<{s["core"]}, {s["pad"]}, '
+            w.append(f'    cfem::stage_rows<{s["core"]}, '
                      f'{s["nrows"]}>({s["name"]}, {src}, {rows}, k0, tid);')
         w.append('    __syncthreads();')
         if nred and (mask & (F | GRAD)):
@@ -364,7 +368,7 @@ class Generator:
                 s = lay['stor'][('lam', fi)]
                 for o in range(f['out_core']):
                     w.append(f'            const double lam_{fi}_{o} = '
-                             f'{s["name"]}[tid * {s["pad"]} + {o}];')
+                             f'{s["name"]}[cfem::Skew<{s["core"]}>::row(tid) + {o}];')
             for slot, code in p['reds']:
                 w.append(f'            red[{self.dyn_index[slot]}] += '
                          f'act ? ({code}) : 0.0;')
@@ -388,7 +392,7 @@ class Generator:
                         w.append(f'                cfem::warp_put<{it.c}>'
                                  f'(wb + {wboff}, lane, o);')
                         staged.append((it, wboff))
-                        wboff += 32 * _pad_odd(it.c)
+                        wboff += _skew_size(it.c, 32)
                     w.append('            }')
                 if staged:
                     w.append('            __syncwarp();')

@@ -5,6 +5,8 @@
 // the structure tables in namespace `gen` and CFEM_TILE, then includes this
 // header, then emits its kernels in terms of the helpers below:
 //
+//   Skew           bank-conflict-free shared-memory layout for arrays that are
+//                  accessed both row-per-thread and flat;
 //   stage_rows     coalesced global -> shared staging of a contiguous slab of
 //                  rows of a row-major [rows][CORE] array (the IPOPT-facing
 //                  decision vector keeps samples row-major, so the slab of one
@@ -12,7 +14,7 @@
 //                  functions read -- is ONE contiguous range of HBM);
 //   warp_put /     per-warp shared-memory transposition of the values one
 //   warp_flush     thread (= one sample) produces for a [rows][C] output block:
-//                  lanes park their C values in a conflict-free padded layout,
+//                  lanes park their C values in the conflict-free Skew layout,
 //                  then the warp streams the 32*C contiguous doubles of the
 //                  block to HBM with unit-stride, full-sector stores;
 //   block_reduce   deterministic warp-shuffle + shared-memory tree reduction of
@@ -49,11 +51,31 @@ __device__ __forceinline__ void stage_contig(double* __restrict__ dst,
     for (int e = tid; e < n; e += CFEM_TILE) dst[e] = __ldg(src + e);
 }
 
+// Bank-conflict-free shared-memory layout of a [rows][C] array of doubles that
+// is written row-wise by one thread per row AND streamed flat (element e of
+// the row-major array by lane e mod 32), or the other way round.  Shared
+// memory has 16 banks of 8 bytes per half-warp phase.  With g = gcd(C, 16) the
+// rows t and t + 16/g collide when stored densely, so every group of
+// m = 16/g rows is skewed by one more double:
+//     addr(t, j) = t*C + j + t/m           (row access: 16 rows -> 16 banks)
+//     addr(e)    = e + e/(C*m)             (flat access: C*m is a multiple of
+//                                           16, so the skew is constant inside
+//                                           an aligned group of 16 elements)
+template <int C>
+struct Skew {
+    static constexpr int gcd16(int c) { return (c % 16 == 0) ? 16 : (c % 8 == 0) ? 8 : (c % 4 == 0) ? 4 : (c % 2 == 0) ? 2 : 1; }
+    static constexpr int g = gcd16(C);
+    static constexpr int m = 16 / g;
+    static constexpr int L = C * m;
+    __host__ __device__ static constexpr int row(int t) { return t * C + t / m; }
+    __host__ __device__ static constexpr int flat(int e) { return e + e / L; }
+    __host__ __device__ static constexpr int size(int rows) { return rows * C + (rows + m - 1) / m; }
+};
+
 // Stage rows [row_begin, row_begin + NROWS) of a row-major [rows_total][CORE]
-// array into shared memory with row pitch PAD (odd pitch => the later
-// one-row-per-thread reads are bank-conflict free).  Rows outside the array
+// array into shared memory in the Skew<CORE> layout.  Rows outside the array
 // are skipped.  Global reads are unit-stride over the contiguous slab.
-template <int CORE, int PAD, int NROWS>
+template <int CORE, int NROWS>
 __device__ __forceinline__ void stage_rows(double* __restrict__ dst,
                                            const double* __restrict__ src,
                                            long long rows_total,
@@ -63,17 +85,14 @@ __device__ __forceinline__ void stage_rows(double* __restrict__ dst,
     long long hi = row_begin + NROWS;
     if (hi > rows_total) hi = rows_total;
     if (hi <= lo) return;
-    const int first = (int)(lo - row_begin);
+    const int first = (int)(lo - row_begin) * CORE;
     const int nelem = (int)(hi - lo) * CORE;
     const double* __restrict__ s = src + lo * CORE;
     constexpr int kIter = (NROWS * CORE + CFEM_TILE - 1) / CFEM_TILE;
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
         const int e = tid + it * CFEM_TILE;
-        if (e < nelem) {
-            const int r = e / CORE, j = e - r * CORE;
-            dst[(first + r) * PAD + j] = __ldg(s + e);
-        }
+        if (e < nelem) dst[Skew<CORE>::flat(first + e)] = __ldg(s + e);
     }
 }
 
@@ -81,19 +100,18 @@ __device__ __forceinline__ void stage_rows(double* __restrict__ dst,
 // per-warp output transposition
 // ---------------------------------------------------------------------------
 
-__host__ __device__ constexpr int pad_odd(int c) { return c | 1; }
-
-// Lane parks its C values of one output block.
+// Lane parks its C values of one output block (row access of Skew<C>).
 template <int C>
 __device__ __forceinline__ void warp_put(double* __restrict__ wb, int lane,
                                          const double (&v)[C])
 {
+    double* __restrict__ row = wb + Skew<C>::row(lane);
 #pragma unroll
-    for (int j = 0; j < C; ++j) wb[lane * pad_odd(C) + j] = v[j];
+    for (int j = 0; j < C; ++j) row[j] = v[j];
 }
 
 // The warp writes the first nvalid*C doubles of the block chunk to HBM,
-// consecutive lanes -> consecutive addresses.
+// consecutive lanes -> consecutive addresses (flat access of Skew<C>).
 template <int C>
 __device__ __forceinline__ void warp_flush(const double* __restrict__ wb,
                                            int lane, double* __restrict__ dst,
@@ -103,10 +121,7 @@ __device__ __forceinline__ void warp_flush(const double* __restrict__ wb,
 #pragma unroll
     for (int it = 0; it < C; ++it) {
         const int e = lane + it * 32;
-        if (e < total) {
-            const int t = e / C, j = e - t * C;
-            __stcs(dst + e, wb[t * pad_odd(C) + j]);
-        }
+        if (e < total) __stcs(dst + e, wb[Skew<C>::flat(e)]);
     }
 }
 
