@@ -254,6 +254,8 @@ class Generator:
         for v in sorted(param_off):
             param_off[v] = off
             off += self.st.vars[v]['core']
+        off += off & 1
+        stage_off = off             # start of staging buffer 0
         for key in sorted(stor):
             s = stor[key]
             if key[0] == 'var':
@@ -266,8 +268,11 @@ class Generator:
             s['nrows'] = self.tile + s['shift']
             s['name'] = f's_{key[0]}{key[1]}'
             off += off & 1      # keep 16-byte alignment of every region
-            s['off'] = off
+            s['off'] = off - stage_off      # relative to the staging buffer
             off += _skew_size(core, s['nrows'])
+        off += off & 1
+        stage_size = off - stage_off
+        off += stage_size           # staging buffer 1 (prefetch target)
         # output passes: group the items of every function under the budget
         wbuf = 0
         for p in plan:
@@ -293,7 +298,8 @@ class Generator:
         wbuf_off = off
         off += warps * wbuf
         return {'param_off': param_off, 'stor': stor, 'red_off': red_off,
-                'wbuf_off': wbuf_off, 'wbuf': wbuf, 'total': off}
+                'wbuf_off': wbuf_off, 'wbuf': wbuf, 'total': off,
+                'stage_off': stage_off, 'stage_size': stage_size}
 
     # ------------------------------------------------------------------
     # emitters
@@ -316,39 +322,70 @@ class Generator:
         w.append('    const int tid = threadIdx.x, lane = tid & 31, '
                  'warp = tid >> 5;')
         w.append('    const long long b = blockIdx.y;')
-        w.append(f'    const long long k0 = (long long)blockIdx.x * {T};')
-        w.append('    const long long kw = k0 + warp * 32;')
-        w.append('    const long long k = k0 + tid;')
         w.append('    const double* __restrict__ dvec = a.dvec + b * a.ndec;')
-        w.append('    (void)lane; (void)kw; (void)k; (void)dvec;')
         w.append('    double* const sp = smem;')
         w.append(f'    double* const wb = smem + {lay["wbuf_off"]} + warp * '
                  f'{lay["wbuf"]};')
-        w.append('    (void)sp; (void)wb;')
-        # staging
+        w.append('    (void)lane; (void)dvec; (void)sp; (void)wb;')
         for v, off in sorted(lay['param_off'].items()):
             w.append(f'    cfem::stage_contig(sp + {off}, dvec + '
                      f'a.var_off[{v}], {self.st.vars[v]["core"]}, tid);')
-        for key in sorted(lay['stor']):
-            s = lay['stor'][key]
-            w.append(f'    double* const {s["name"]} = smem + {s["off"]};')
-            if key[0] == 'var':
-                src = f'dvec + a.var_off[{key[1]}]'
-                rows = f'a.var_rows[{key[1]}]'
-            elif key[0] == 'data':
-                src = (f'a.data[{key[1]}] + b * a.data_rows[{key[1]}] * '
-                       f'{s["core"]}')
-                rows = f'a.data_rows[{key[1]}]'
-            else:
-                ci = self.funs[key[1]]['cons_index']
-                src = f'a.lam + b * a.ncons + a.cons_off[{ci}]'
-                rows = f'a.fun_rows[{key[1]}]'
-            w.append(f'    cfem::stage_rows<{s["core"]}, '
-                     f'{s["nrows"]}>({s["name"]}, {src}, {rows}, k0, tid);')
+        if mask & (F | GRAD):
+            w.append(f'    double red[{max(nred, 1)}];')
+            w.append(f'    for (int r = 0; r < {max(nred, 1)}; ++r) '
+                     'red[r] = 0.0;')
+
+        def stage(tile_expr, buf_expr):
+            """cp.async of one tile's rows into staging buffer buf_expr."""
+            out = ['        {',
+                   f'            double* const stg = smem + '
+                   f'{lay["stage_off"]} + ({buf_expr}) * {lay["stage_size"]};',
+                   f'            const long long r0 = ({tile_expr}) * {T};',
+                   '            (void)stg; (void)r0;']
+            for key in sorted(lay['stor']):
+                st_ = lay['stor'][key]
+                if key[0] == 'var':
+                    src = f'dvec + a.var_off[{key[1]}]'
+                    rows = f'a.var_rows[{key[1]}]'
+                elif key[0] == 'data':
+                    src = (f'a.data[{key[1]}] + b * a.data_rows[{key[1]}] * '
+                           f'{st_["core"]}')
+                    rows = f'a.data_rows[{key[1]}]'
+                else:
+                    ci = self.funs[key[1]]['cons_index']
+                    src = f'a.lam + b * a.ncons + a.cons_off[{ci}]'
+                    rows = f'a.fun_rows[{key[1]}]'
+                out.append(f'            cfem::stage_rows_async<{st_["core"]}, '
+                           f'{st_["nrows"]}>(stg + {st_["off"]}, {src}, '
+                           f'{rows}, r0, tid);')
+            out.append('        }')
+            return out
+
+        # persistent CTAs: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the
+        # inputs of the next tile are in flight (cp.async) while this one is
+        # evaluated and streamed out
+        w.append('    const long long tstride = gridDim.x;')
+        w.append('    long long tile = blockIdx.x;')
+        w.append('    int buf = 0;')
+        w.append('    if (tile < a.ntiles)')
+        w += stage('tile', '0')
+        w.append('    cfem::cp_async_commit();')
+        w.append('    for (; tile < a.ntiles; tile += tstride, buf ^= 1) {')
+        w.append('    if (tile + tstride < a.ntiles)')
+        w += stage('tile + tstride', 'buf ^ 1')
+        w.append('    cfem::cp_async_commit();')
+        w.append('    cfem::cp_async_wait<1>();      // this tile has landed')
         w.append('    __syncthreads();')
-        if nred and (mask & (F | GRAD)):
-            w.append(f'    double red[{nred}];')
-            w.append(f'    for (int r = 0; r < {nred}; ++r) red[r] = 0.0;')
+        w.append(f'    double* const stg = smem + {lay["stage_off"]} + buf * '
+                 f'{lay["stage_size"]};')
+        w.append(f'    const long long k0 = tile * {T};')
+        w.append('    const long long kw = k0 + warp * 32;')
+        w.append('    const long long k = k0 + tid;')
+        w.append('    (void)stg; (void)kw; (void)k;')
+        for key in sorted(lay['stor']):
+            st_ = lay['stor'][key]
+            w.append(f'    const double* const {st_["name"]} = stg + '
+                     f'{st_["off"]};')
         for p in plan:
             fi = p['fi']
             f = self.funs[fi]
@@ -404,9 +441,10 @@ class Generator:
             w += ['        ' + u for u in undefs]
             w.append('        }')
             w.append('    }')
+        w.append('    __syncthreads();       // staging buffer is refilled '
+                 'by the next prefetch')
+        w.append('    }   // tile loop')
         if mask & (F | GRAD):
-            if not nred:
-                w.append('    double red[1] = {0.0};')
             w.append(f'    if (cfem::tree_reduce<{max(nred, 1)}>(a, b, red, smem + '
                      f'{lay["red_off"]}, tid)) {{')
             w.append('        // this CTA retired last: it finalises (fixed '
@@ -695,20 +733,38 @@ class Generator:
         w += kernels
         w.append(f'constexpr int kNumParamEntries = {self.n_param_entries};')
         w.append(launch_param_sig + ';    // parameter-only unit')
+        w.append(f'static int g_ctas_per_sm[{len(self.masks)}];')
         w.append('static cudaError_t configure_kernels()')
         w.append('{')
         w.append('    cudaError_t e = cudaSuccess;')
-        for m in self.masks:
+        for i, m in enumerate(self.masks):
             if smem[m] > 48 * 1024:
                 w.append(f'    e = cudaFuncSetAttribute(cfem_sample_kernel_m{m}, '
                          'cudaFuncAttributeMaxDynamicSharedMemorySize, '
                          f'(int)kSmemBytes_m{m});')
                 w.append('    if (e != cudaSuccess) return e;')
+            w.append('    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor('
+                     f'&g_ctas_per_sm[{i}], cfem_sample_kernel_m{m}, CFEM_TILE, '
+                     f'kSmemBytes_m{m});')
+            w.append('    if (e != cudaSuccess) return e;')
+            w.append(f'    if (g_ctas_per_sm[{i}] < 1) g_ctas_per_sm[{i}] = 1;')
         w.append('    return e;')
         w.append('}')
-        w.append('static cudaError_t launch_sample(unsigned mask, dim3 grid, '
-                 'cudaStream_t s, const cfem::KArgs& a)')
+        w.append('// Persistent launch: at most `max_ctas` CTAs per problem '
+                 '(resident CTAs per SM x SMs x waves), each looping over tiles.')
+        w.append('static cudaError_t launch_sample(unsigned mask, int batch, '
+                 'int sm_count, int waves, cudaStream_t s, cfem::KArgs a)')
         w.append('{')
+        w.append('    int per_sm = 1;')
+        w.append('    for (int i = 0; i < kNumMasks; ++i) '
+                 'if (kMasks[i] == mask) per_sm = g_ctas_per_sm[i];')
+        w.append('    long long gx = (long long)per_sm * sm_count * waves / batch;')
+        w.append('    if (gx < 1) gx = 1;')
+        w.append('    if (gx > a.ntiles) gx = a.ntiles;')
+        w.append('    a.nctas = gx;')
+        w.append('    a.ngroups = (gx + cfem::kReduceGroup - 1) / '
+                 'cfem::kReduceGroup;')
+        w.append('    const dim3 grid((unsigned)gx, (unsigned)batch);')
         w.append('    switch (mask) {')
         for m in self.masks:
             w.append(f'    case {m}u: cfem_sample_kernel_m{m}<<<grid, CFEM_TILE, '

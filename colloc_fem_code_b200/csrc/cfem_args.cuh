@@ -28,7 +28,8 @@ struct KArgs {
     double* hess;
     double* partials;       // [batch][ntiles][nreduce]
     // two-level deterministic reduction tree (all counters zero between launches)
-    long long     ngroups;      // ceil(ntiles / kReduceGroup)
+    long long     nctas;        // CTAs per problem of this launch (<= ntiles)
+    long long     ngroups;      // ceil(nctas / kReduceGroup)
     double*       gpartials;    // [batch][ngroups][nreduce]
     unsigned int* group_count;  // [batch][ngroups] CTAs retired per group
     unsigned int* done_count;   // [batch] groups retired per problem

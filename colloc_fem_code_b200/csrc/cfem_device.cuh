@@ -96,6 +96,45 @@ __device__ __forceinline__ void stage_rows(double* __restrict__ dst,
     }
 }
 
+// Asynchronous variant (cp.async, 8-byte granules: the IPOPT-facing arrays are
+// only 8-byte aligned): the copy goes global -> shared without passing through
+// registers, so a tile can be prefetched while the previous one is processed.
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory");
+}
+
+template <int CORE, int NROWS>
+__device__ __forceinline__ void stage_rows_async(double* __restrict__ dst,
+                                                 const double* __restrict__ src,
+                                                 long long rows_total,
+                                                 long long row_begin, int tid)
+{
+    long long lo = row_begin < 0 ? 0 : row_begin;
+    long long hi = row_begin + NROWS;
+    if (hi > rows_total) hi = rows_total;
+    if (hi <= lo) return;
+    const int first = (int)(lo - row_begin) * CORE;
+    const int nelem = (int)(hi - lo) * CORE;
+    const double* __restrict__ s = src + lo * CORE;
+    constexpr int kIter = (NROWS * CORE + CFEM_TILE - 1) / CFEM_TILE;
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+        const int e = tid + it * CFEM_TILE;
+        if (e < nelem) cp_async8(dst + Skew<CORE>::flat(first + e), s + e);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // per-warp output transposition
 // ---------------------------------------------------------------------------
@@ -214,9 +253,10 @@ __device__ __forceinline__ double reduce_tiles(const double* __restrict__ part,
 
 // Two-level reduction of the per-thread partial sums `v` of every CTA of
 // problem `b` (objective and parameter-gradient terms):
-//   level 0  CTA tree (warp shuffles + shared memory) -> partials[tile]
-//   level 1  the last CTA of every group of kReduceGroup tiles to retire sums
-//            the group's partials in tile order       -> gpartials[group]
+//   level 0  per thread over the CTA's tiles, then CTA tree (warp shuffles +
+//            shared memory)                             -> partials[cta]
+//   level 1  the last CTA of every group of kReduceGroup CTAs to retire sums
+//            the group's partials in CTA order          -> gpartials[group]
 //   level 2  the last group to retire returns true: its CTA sums gpartials in
 //            group order (cfem_finalize in the generated code).
 // No floating-point atomics and a fixed association order: bitwise
@@ -228,11 +268,11 @@ __device__ __forceinline__ bool tree_reduce(const KArgs& a, long long b,
                                             double* __restrict__ scratch,
                                             int tid)
 {
-    const long long tile = blockIdx.x;
-    block_reduce_store<R>(v, scratch, a.partials + (b * a.ntiles + tile) * R, tid);
-    const long long g = tile / kReduceGroup;
+    const long long cta = blockIdx.x;       // one partial per (persistent) CTA
+    block_reduce_store<R>(v, scratch, a.partials + (b * a.ntiles + cta) * R, tid);
+    const long long g = cta / kReduceGroup;
     const long long first = g * kReduceGroup;
-    const long long left = a.ntiles - first;
+    const long long left = a.nctas - first;
     const unsigned in_group = left < kReduceGroup ? (unsigned)left : (unsigned)kReduceGroup;
     unsigned int* gcount = a.group_count + b * a.ngroups + g;
     if (!last_block_done(gcount, in_group, tid)) return false;

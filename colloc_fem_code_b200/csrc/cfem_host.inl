@@ -18,6 +18,8 @@
 
 struct cfem_problem {
     int           device = 0;
+    int           sm_count = 1;
+    int           waves = 1;            // CTAs launched = resident CTAs x waves
     cudaStream_t  stream = nullptr;
     bool          own_stream = false;
     cudaStream_t  aux_stream = nullptr;     // parameter-only kernel, concurrent
@@ -207,6 +209,8 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
         return cfem::fail(nullptr, CFEM_EINVAL, "cfem_create: no such CUDA device",
                           cudaSuccess);
     CFEM_CUDA(nullptr, cudaSetDevice(device));
+    int sm_count = 0;
+    CFEM_CUDA(nullptr, cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     cudaError_t ce = gen::configure_kernels();
     if (ce != cudaSuccess)
         return cfem::fail(nullptr, CFEM_ECUDA, "configure_kernels", ce);
@@ -214,6 +218,8 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     cfem_problem* p = new (std::nothrow) cfem_problem();
     if (!p) return cfem::fail(nullptr, CFEM_ENOMEM, "cfem_create: host allocation", cudaSuccess);
     p->device = device;
+    p->sm_count = sm_count;
+    if (const char* w = getenv("CFEM_WAVES")) { p->waves = atoi(w) > 0 ? atoi(w) : 1; }
     p->N = n_samples;
     p->batch = batch;
     p->halo = halo;
@@ -388,7 +394,6 @@ int cfem_eval(cfem_problem* p, uint32_t what)
     const unsigned mask = cfem::pick_mask(what);
     if (!mask) return cfem::fail(p, CFEM_EINVAL, "cfem_eval: no kernel for this selector", cudaSuccess);
     CFEM_CUDA(p, cudaSetDevice(p->device));
-    const dim3 grid((unsigned)p->k.ntiles, (unsigned)p->batch);
     // The parameter-only functions are independent of the per-sample pass:
     // fork them onto the auxiliary stream so that they overlap it.
     const bool params = gen::kNumParamEntries > 0 &&
@@ -401,7 +406,7 @@ int cfem_eval(cfem_problem* p, uint32_t what)
         p->launches += 1;
     }
     if (p->timing) CFEM_CUDA(p, cudaEventRecord(p->kev[0], p->stream));
-    CFEM_CUDA(p, gen::launch_sample(mask, grid, p->stream, p->k));
+    CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->stream, p->k));
     if (p->timing) {
         CFEM_CUDA(p, cudaEventRecord(p->kev[1], p->stream));
         p->kev_valid = true;
