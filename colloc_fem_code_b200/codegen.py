@@ -51,16 +51,22 @@ def _skew_size(c, rows):
 class _Item:
     """One output block a sample kernel produces for one function."""
 
-    def __init__(self, c, codes, dest, mult=None):
+    def __init__(self, c, codes, dest, mult=None, uniform=False, deps=()):
         self.c = c              # doubles per sample
         self.codes = codes      # C expression per element
         self.dest = dest        # C expression: pointer to row 0 of the block
         self.mult = mult        # optional C expressions multiplied in
+        # every entry is the same for all samples (constants / parameters /
+        # obj_factor): the block is a periodic pattern, streamed from a small
+        # per-CTA table without the per-sample transposition
+        self.uniform = uniform
+        self.deps = list(deps)  # (arg, flat) symbols the entries use
+        self.pat_off = None     # offset of the pattern in the CTA's table
 
 
 class Generator:
     def __init__(self, structure, tile=None, pass_budget=None, masks=None,
-                 min_blocks=None):
+                 min_blocks=None, experiment=None):
         self.st = structure
         self.masks = tuple(masks or DEFAULT_MASKS)
         self.funs = structure.funs
@@ -82,6 +88,8 @@ class Generator:
         self.pass_budget = pass_budget
         self.min_blocks = min_blocks or int(
             os.environ.get('CFEM_MIN_BLOCKS', 0))
+        # tuning experiments only (tools/sweep.py): 'nostore' / 'noload'
+        self.experiment = experiment
         self._reduce_slots()
 
     # ------------------------------------------------------------------
@@ -210,11 +218,14 @@ class Generator:
                         f'a.g + b * a.ncons + a.cons_off[{ci}]'))
                 if mask & JAC:
                     for bi, blk in jac_of.get(fi, []):
-                        for e in blk['entries']:
-                            deps += e.deps
+                        bdeps = [d for e in blk['entries'] for d in e.deps]
+                        uni = blk['c'] > 1 and not self._is_sample_dep(f, bdeps)
+                        if not uni:
+                            deps += bdeps
                         items.append(_Item(
                             blk['c'], [e.code for e in blk['entries']],
-                            f'a.jac + b * a.nnz_jac + a.jac_off[{bi}]'))
+                            f'a.jac + b * a.nnz_jac + a.jac_off[{bi}]',
+                            uniform=uni, deps=bdeps))
             if mask & HESS:
                 for bi, blk in hess_of.get(fi, []):
                     if f['is_objective']:
@@ -223,11 +234,15 @@ class Generator:
                         mult = [f'lam_{fi}_{e.index[2]}'
                                 for e in blk['entries']]
                         lam_needed = True
-                    for e in blk['entries']:
-                        deps += e.deps
+                    bdeps = [d for e in blk['entries'] for d in e.deps]
+                    uni = (f['is_objective'] and blk['c'] > 1
+                           and not self._is_sample_dep(f, bdeps))
+                    if not uni:
+                        deps += bdeps
                     items.append(_Item(
                         blk['c'], [e.code for e in blk['entries']],
-                        f'a.hess + b * a.nnz_hess + a.hess_off[{bi}]', mult))
+                        f'a.hess + b * a.nnz_hess + a.hess_off[{bi}]', mult,
+                        uniform=uni, deps=bdeps))
             if items or reds:
                 plan.append({'fi': fi, 'items': items, 'reds': reds,
                              'deps': sorted(set(deps)),
@@ -241,7 +256,8 @@ class Generator:
         stor = {}
         for p in plan:
             f = self.funs[p['fi']]
-            for a, _ in p['deps']:
+            udeps = [d for it in p['items'] if it.uniform for d in it.deps]
+            for a, _ in list(p['deps']) + udeps:
                 ref = f['args'][a]
                 if ref[0] == 'param' and ref[1] not in param_off:
                     param_off[ref[1]] = None
@@ -254,6 +270,13 @@ class Generator:
         for v in sorted(param_off):
             param_off[v] = off
             off += self.st.vars[v]['core']
+        off += off & 1
+        pat_off = off               # periodic patterns of the uniform blocks
+        for p in plan:
+            for it in p['items']:
+                if it.uniform:
+                    it.pat_off = off - pat_off
+                    off += it.c
         off += off & 1
         stage_off = off             # start of staging buffer 0
         for key in sorted(stor):
@@ -278,6 +301,8 @@ class Generator:
         for p in plan:
             passes, cur, used = [], [], 0
             for it in p['items']:
+                if it.uniform:
+                    continue        # streamed from the pattern table
                 need = 0 if it.c == 1 else it.c + 1
                 if cur and used + need > self.pass_budget:
                     passes.append(cur)
@@ -287,6 +312,7 @@ class Generator:
             if cur:
                 passes.append(cur)
             p['passes'] = passes
+            p['uniform'] = [it for it in p['items'] if it.uniform]
             for ps in passes:
                 wbuf = max(wbuf, sum(0 if it.c == 1 else _skew_size(it.c, 32)
                                      for it in ps))
@@ -299,7 +325,8 @@ class Generator:
         off += warps * wbuf
         return {'param_off': param_off, 'stor': stor, 'red_off': red_off,
                 'wbuf_off': wbuf_off, 'wbuf': wbuf, 'total': off,
-                'stage_off': stage_off, 'stage_size': stage_size}
+                'stage_off': stage_off, 'stage_size': stage_size,
+                'pat_off': pat_off}
 
     # ------------------------------------------------------------------
     # emitters
@@ -334,6 +361,22 @@ class Generator:
             w.append(f'    double red[{max(nred, 1)}];')
             w.append(f'    for (int r = 0; r < {max(nred, 1)}; ++r) '
                      'red[r] = 0.0;')
+        w.append(f'    double* const pat = smem + {lay["pat_off"]};')
+        w.append('    (void)pat;')
+        if any(p['uniform'] for p in plan):
+            w.append('    __syncthreads();       // parameters are staged')
+            w.append('    if (tid == 0) {        // once per (persistent) CTA')
+            for p in plan:
+                f = self.funs[p['fi']]
+                for it in p['uniform']:
+                    defs, undefs = self._define_args(f, it.deps, 'sample', lay)
+                    w += defs
+                    for j, code in enumerate(it.codes):
+                        if it.mult:
+                            code = f'({it.mult[j]}) * ({code})'
+                        w.append(f'        pat[{it.pat_off + j}] = {code};')
+                    w += undefs
+            w.append('    }')
 
         def stage(tile_expr, buf_expr):
             """cp.async of one tile's rows into staging buffer buf_expr."""
@@ -409,6 +452,10 @@ class Generator:
             for slot, code in p['reds']:
                 w.append(f'            red[{self.dyn_index[slot]}] += '
                          f'act ? ({code}) : 0.0;')
+            for it in p['uniform']:
+                w.append(f'            cfem::warp_store_periodic<{it.c}>(pat + '
+                         f'{it.pat_off}, lane, ({it.dest}) + kw * {it.c}, '
+                         'nvalid);')
             for ps in p['passes']:
                 wboff = 0
                 staged = []
@@ -722,6 +769,8 @@ class Generator:
 
         # ---- main unit
         w = list(head)
+        if self.experiment:
+            w.append(f'#define CFEM_EXPERIMENT_{self.experiment.upper()} 1')
         w.append(f'#define CFEM_TILE {self.tile}')
         w += tables
         w.append('namespace gen {')

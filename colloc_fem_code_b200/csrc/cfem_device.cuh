@@ -131,7 +131,9 @@ __device__ __forceinline__ void stage_rows_async(double* __restrict__ dst,
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
         const int e = tid + it * CFEM_TILE;
+#ifndef CFEM_EXPERIMENT_NOLOAD
         if (e < nelem) cp_async8(dst + Skew<CORE>::flat(first + e), s + e);
+#endif
     }
 }
 
@@ -150,17 +152,60 @@ __device__ __forceinline__ void warp_put(double* __restrict__ wb, int lane,
 }
 
 // The warp writes the first nvalid*C doubles of the block chunk to HBM,
-// consecutive lanes -> consecutive addresses (flat access of Skew<C>).
+// consecutive lanes -> consecutive addresses (flat access of Skew<C>).  The
+// full-warp case (all but the last tile) runs without predicates.
 template <int C>
 __device__ __forceinline__ void warp_flush(const double* __restrict__ wb,
                                            int lane, double* __restrict__ dst,
                                            int nvalid)
 {
-    const int total = nvalid * C;
+#ifdef CFEM_EXPERIMENT_NOSTORE      // tuning experiment: everything but the store
+#define CFEM_ST(ptr, val) do { const double v_ = (val); if (v_ == 1.2345e300) __stcs((ptr), v_); } while (0)
+#else
+#define CFEM_ST(ptr, val) __stcs((ptr), (val))
+#endif
+    const double* __restrict__ src = wb + lane;
+    double* __restrict__ out = dst + lane;
+    if (nvalid == 32) {
 #pragma unroll
-    for (int it = 0; it < C; ++it) {
-        const int e = lane + it * 32;
-        if (e < total) __stcs(dst + e, wb[Skew<C>::flat(e)]);
+        for (int it = 0; it < C; ++it) {
+            const int e = lane + it * 32;
+            CFEM_ST(out + it * 32, src[it * 32 + e / Skew<C>::L]);
+        }
+    } else {
+        const int total = nvalid * C;
+#pragma unroll
+        for (int it = 0; it < C; ++it) {
+            const int e = lane + it * 32;
+            if (e < total) CFEM_ST(out + it * 32, src[it * 32 + e / Skew<C>::L]);
+        }
+    }
+}
+
+// A block whose C entries are the same for every sample is a periodic stream:
+// element e of the chunk is pat[e mod C].  No per-sample work and no
+// transposition: the warp reads the C-entry pattern table and streams.
+template <int C>
+__device__ __forceinline__ void warp_store_periodic(const double* __restrict__ pat,
+                                                    int lane, double* __restrict__ dst,
+                                                    int nvalid)
+{
+    double* __restrict__ out = dst + lane;
+    const int total = nvalid * C;
+    if constexpr (32 % C == 0) {
+        const double v = pat[lane % C];     // the same entry for every chunk row
+#pragma unroll
+        for (int it = 0; it < C; ++it)
+            if (lane + it * 32 < total) CFEM_ST(out + it * 32, v);
+    } else {
+        constexpr int kStep = 32 % C;
+        int idx = lane % C;
+#pragma unroll
+        for (int it = 0; it < C; ++it) {
+            if (lane + it * 32 < total) CFEM_ST(out + it * 32, pat[idx]);
+            idx += kStep;
+            if (idx >= C) idx -= C;
+        }
     }
 }
 
@@ -168,7 +213,7 @@ __device__ __forceinline__ void warp_flush(const double* __restrict__ wb,
 __device__ __forceinline__ void lane_store(double* __restrict__ dst, int lane,
                                            int nvalid, double v)
 {
-    if (lane < nvalid) __stcs(dst + lane, v);
+    if (lane < nvalid) CFEM_ST(dst + lane, v);
 }
 
 // ---------------------------------------------------------------------------

@@ -21,12 +21,13 @@ KIND = os.environ.get('SWEEP_KIND', 'ml')
 DIMS = tuple(int(c) for c in os.environ.get('SWEEP_DIMS', '212'))
 N = int(os.environ.get('SWEEP_N', 1_000_000))
 VARIANTS = []
-for t, b in itertools.product((32, 64, 128), (4, 8)):
-    for warps in (0, 48, 64):       # resident warps per SM asked of ptxas
-        mb = min(32, warps * 32 // t)
-        v = dict(tile=t, pass_budget=b, min_blocks=mb)
-        if v not in VARIANTS:
-            VARIANTS.append(v)
+for t in (32, 64, 128, 256):
+    VARIANTS.append(dict(tile=t, pass_budget=6))
+VARIANTS += [dict(tile=64, pass_budget=6, experiment='nostore'),
+             dict(tile=64, pass_budget=6, experiment='noload'),
+             dict(tile=128, pass_budget=6, experiment='nostore'),
+             dict(tile=128, pass_budget=6, experiment='noload')]
+WAVES = [int(w) for w in os.environ.get('SWEEP_WAVES', '1,2,4,8').split(',')]
 
 
 def problem():
@@ -60,7 +61,8 @@ def run():
     import bench
     balg = bench.algorithmic_bytes_per_sample(nx, nu, ny)
     out = []
-    for v in VARIANTS:
+    for v, waves in itertools.product(VARIANTS, WAVES):
+        os.environ['CFEM_WAVES'] = str(waves)
         lib = backend.Library.load(backend.build_library(
             st, backend.structure_label(st), masks=(31,), **v))
         h = backend.Handle(lib, st.N, [d['source'] for d in st.data],
@@ -75,7 +77,7 @@ def run():
             h.eval(31)
             ms.append(h.last_sample_kernel_ms())
         ms = ms[3:]
-        rec = dict(v, ms_min=min(ms), ms_med=float(np.median(ms)),
+        rec = dict(v, waves=waves, ms_min=min(ms), ms_med=float(np.median(ms)),
                    gbs=balg * N / (np.median(ms) * 1e-3) / 1e9)
         print(json.dumps(rec), flush=True)
         out.append(rec)
