@@ -66,7 +66,7 @@ class _Item:
 
 class Generator:
     def __init__(self, structure, tile=None, pass_budget=None, masks=None,
-                 min_blocks=None, experiment=None):
+                 min_blocks=None, experiment=None, store=None):
         self.st = structure
         self.masks = tuple(masks or DEFAULT_MASKS)
         self.funs = structure.funs
@@ -74,13 +74,10 @@ class Generator:
                             if f['per_sample']]
         self.param_funs = [i for i, f in enumerate(self.funs)
                            if not f['per_sample']]
-        inputs = sum(v['core'] for v in structure.vars if v['per_sample']) \
-            + sum(d['core'] for d in structure.data) \
-            + sum(self.funs[i]['out_core'] for i in self.sample_funs
-                  if not self.funs[i]['is_objective'])
+        # defaults from the B200 sweeps (profiles/README.md): 128-sample tiles,
+        # output passes of <= 6 doubles per lane
         if tile is None:
-            tile = int(os.environ.get('CFEM_TILE', 0)) or \
-                (64 if inputs <= 16 else 128)
+            tile = int(os.environ.get('CFEM_TILE', 0)) or 128
         if pass_budget is None:
             pass_budget = int(os.environ.get('CFEM_PASS_BUDGET', 0)) or 6
         assert tile % 32 == 0 and 32 <= tile <= 1024
@@ -90,6 +87,7 @@ class Generator:
             os.environ.get('CFEM_MIN_BLOCKS', 0))
         # tuning experiments only (tools/sweep.py): 'nostore' / 'noload'
         self.experiment = experiment
+        self.store = store          # None (st.global.cs) | 'wb' | 'cg' | 'wt'
         self._reduce_slots()
 
     # ------------------------------------------------------------------
@@ -771,6 +769,10 @@ class Generator:
         w = list(head)
         if self.experiment:
             w.append(f'#define CFEM_EXPERIMENT_{self.experiment.upper()} 1')
+        if self.store:
+            op = {'wb': '(*(ptr) = (val))', 'cg': '__stcg((ptr), (val))',
+                  'wt': '__stwt((ptr), (val))'}[self.store]
+            w.append(f'#define CFEM_STORE_OP(ptr, val) {op}')
         w.append(f'#define CFEM_TILE {self.tile}')
         w += tables
         w.append('namespace gen {')

@@ -159,10 +159,13 @@ __device__ __forceinline__ void warp_flush(const double* __restrict__ wb,
                                            int lane, double* __restrict__ dst,
                                            int nvalid)
 {
+#ifndef CFEM_STORE_OP               // streaming (evict-first) stores by default
+#define CFEM_STORE_OP(ptr, val) __stcs((ptr), (val))
+#endif
 #ifdef CFEM_EXPERIMENT_NOSTORE      // tuning experiment: everything but the store
-#define CFEM_ST(ptr, val) do { const double v_ = (val); if (v_ == 1.2345e300) __stcs((ptr), v_); } while (0)
+#define CFEM_ST(ptr, val) do { const double v_ = (val); if (v_ == 1.2345e300) CFEM_STORE_OP((ptr), v_); } while (0)
 #else
-#define CFEM_ST(ptr, val) __stcs((ptr), (val))
+#define CFEM_ST(ptr, val) CFEM_STORE_OP((ptr), (val))
 #endif
     const double* __restrict__ src = wb + lane;
     double* __restrict__ out = dst + lane;

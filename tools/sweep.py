@@ -21,13 +21,11 @@ KIND = os.environ.get('SWEEP_KIND', 'ml')
 DIMS = tuple(int(c) for c in os.environ.get('SWEEP_DIMS', '212'))
 N = int(os.environ.get('SWEEP_N', 1_000_000))
 VARIANTS = []
-for t in (32, 64, 128, 256):
-    VARIANTS.append(dict(tile=t, pass_budget=6))
-VARIANTS += [dict(tile=64, pass_budget=6, experiment='nostore'),
-             dict(tile=64, pass_budget=6, experiment='noload'),
-             dict(tile=128, pass_budget=6, experiment='nostore'),
-             dict(tile=128, pass_budget=6, experiment='noload')]
-WAVES = [int(w) for w in os.environ.get('SWEEP_WAVES', '1,2,4,8').split(',')]
+for st_ in (None, 'wb', 'cg'):
+    VARIANTS.append(dict(tile=128, pass_budget=6, store=st_))
+    VARIANTS.append(dict(tile=128, pass_budget=6, store=st_,
+                         experiment='noload'))
+WAVES = [int(w) for w in os.environ.get('SWEEP_WAVES', '4,8').split(',')]
 
 
 def problem():
@@ -69,7 +67,8 @@ def run():
                            st.scalar_values)
         h.set_kernel_timing(True)
         h.set_dvec(dvec)
-        h.set_multipliers(sigma, lam)
+        lam_h = lam if h.ncons == lam.size else np.resize(lam, h.ncons)
+        h.set_multipliers(sigma, lam_h)
         ms = []
         for i in range(13):
             h.flush_l2(256 << 20)
