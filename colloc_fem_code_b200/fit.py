@@ -326,3 +326,31 @@ class _StructureOnly:
 
     def time_structure(self):
         return self._ts(self)
+
+
+def balanced_guess(A, B, C):
+    """Balanced realisation of (A, B, C) and the square-root Gramian variables
+    of the reference's balancing constraints (/root/reference/symfem.py:94-108):
+
+        sW ctrl_orth = [A sW, B],   sW obs_orth = [A' sW, C'],
+
+    rows of ``ctrl_orth`` / ``obs_orth`` orthonormal, i.e. the controllability
+    and observability Gramians both equal ``diag(sW_diag)**2``.  Returns
+    ``(T, values)`` with ``x_balanced = T^-1 x`` and the decision-variable
+    values ``A B C sW_diag ctrl_orth obs_orth`` in balanced coordinates.
+    """
+    import scipy.linalg as sla
+    A, B, C = (np.asarray(m, float) for m in (A, B, C))
+    Wc = sla.solve_discrete_lyapunov(A, B @ B.T)
+    Wo = sla.solve_discrete_lyapunov(A.T, C.T @ C)
+    Lc = np.linalg.cholesky(Wc)
+    Lo = np.linalg.cholesky(Wo)
+    U, sv, Vt = np.linalg.svd(Lo.T @ Lc)
+    T = Lc @ Vt.T / np.sqrt(sv)             # balancing transformation
+    Ti = (U / np.sqrt(sv)).T @ Lo.T
+    Ab, Bb, Cb = Ti @ A @ T, Ti @ B, C @ T
+    sW = np.sqrt(sv)
+    ctrl_orth = np.hstack((Ab * sW, Bb)) / sW[:, None]
+    obs_orth = np.hstack((Ab.T * sW, Cb.T)) / sW[:, None]
+    return T, {'A': Ab, 'B': Bb, 'C': Cb, 'sW_diag': sW,
+               'ctrl_orth': ctrl_orth, 'obs_orth': obs_orth}

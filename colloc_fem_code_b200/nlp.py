@@ -337,14 +337,20 @@ class BorderedBandKKT:
             Kbb = Kb[:, inner]
             lu = spla.splu(Kbb.tocsc(), permc_spec='NATURAL')
             if len(border):
-                Kbp = Kb[:, border].toarray()
+                # only the border columns that touch the samples (the model
+                # parameters proper) need a banded solve
+                Kbp_s = Kb[:, border].tocsc()
+                cpl = np.flatnonzero(np.diff(Kbp_s.indptr))
                 Kp = K[border]
                 Kpb = Kp[:, inner]
-                Y = lu.solve(Kbp)
-                S = Kp[:, border].toarray() - Kpb @ Y
+                S = Kp[:, border].toarray()
+                if len(cpl):
+                    Y = lu.solve(Kbp_s[:, cpl].toarray())
+                    S[:, cpl] -= Kpb @ Y
                 zb = lu.solve(rhs[inner])
                 zp = np.linalg.solve(S, rhs[border] - Kpb @ zb)
-                zb = zb - Y @ zp
+                if len(cpl):
+                    zb = zb - Y @ zp[cpl]
             else:
                 S = np.zeros((0, 0))
                 zb, zp = lu.solve(rhs[inner]), np.zeros(0)
