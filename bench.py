@@ -184,16 +184,19 @@ def run_reference(args):
     }))
 
 
-def workload_config(world):
+def workload_config(world, reduce_mode='none'):
     nx, nu, ny = DIMS
+    how = {'peer': 'objective + parameter gradient reduced inside the kernel '
+                   'over NVLink peer memory (no NCCL call on the path)',
+           'nccl': 'NCCL allreduce of objective + parameter gradient',
+           'none': ''}[reduce_mode]
     return {
         'workload': ('attas_sp_ml: MaximumLikelihoodDT (nx,nu,ny)=(2,1,2), '
                      f'synthetic trajectory, N={N_PER_GPU} samples per GPU'),
         'family': KIND, 'dims': list(DIMS),
         'n_samples_total': N_PER_GPU * world,
         'parallelism': 'single GPU' if world == 1 else
-        f'time-sharded x{world}, 1-sample halo, NCCL allreduce of objective '
-        '+ parameter gradient',
+        f'time-sharded x{world}, 1-sample halo, {how}',
         'l2': f'flushed between timed steps ({FLUSH_BYTES >> 20} MiB memset, '
               'outside the per-step events); working set per step '
               f'{algorithmic_bytes_per_sample(nx, nu, ny) * N_PER_GPU / 1e6:.0f}'
@@ -268,11 +271,29 @@ def run_ours(args):
     ptrs = h.device_ptrs()
     red = torch.as_tensor(CudaArray(ptrs['reduce'], ev.n_reduce),
                           device=f'cuda:{local_rank}')
+    # cross-GPU reduction of [f, d f/d params]: fused into the kernel over
+    # NVLink peer memory; CFEM_REDUCE=nccl selects all_reduce + a second kernel
+    reduce_mode = 'none'
+    if world > 1:
+        reduce_mode = os.environ.get('CFEM_REDUCE', 'peer')
+        if reduce_mode == 'peer':
+            try:
+                ev.enable_peer_reduce()
+            except Exception as exc:        # no P2P / symmetric memory
+                print(f'rank {rank}: peer reduce unavailable ({exc!r}); '
+                      'using NCCL', file=sys.stderr)
+                reduce_mode = 'nccl'
+        flags = torch.tensor([reduce_mode == 'peer'], dtype=torch.int32,
+                             device=f'cuda:{local_rank}')
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        if reduce_mode == 'peer' and int(flags.item()) == 0:
+            h.set_peers(0, 1, [], [])
+            reduce_mode = 'nccl'
 
     def device_step():
         h.set_dvec_device(d_dvec.data_ptr())      # "new x": invalidates
         h.eval(backend.ALL)
-        if world > 1:
+        if reduce_mode == 'nccl':
             dist.all_reduce(red)
             h.apply_reduced(ptrs['reduce'])
 
@@ -321,7 +342,7 @@ def run_ours(args):
         h.set_dvec(host.dvec)
         h.set_multipliers(sigma, host.lam)
         h.eval(backend.ALL)
-        if world > 1:
+        if reduce_mode == 'nccl':
             dist.all_reduce(red)
             h.apply_reduced(ptrs['reduce'])
         host.fetch_all()
@@ -356,7 +377,8 @@ def run_ours(args):
             'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic', 'config': workload_config(world),
+            'data': 'synthetic',
+            'config': workload_config(world, reduce_mode),
             'samples_per_s': value * N_PER_GPU,
             'gpu_launches': int(launches),
             'wall_s_timed_region': wall,

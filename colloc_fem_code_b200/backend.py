@@ -79,6 +79,12 @@ ABI = {
     'cfem_device_ptrs': (ctypes.c_int, [ctypes.c_void_p]
                          + [ctypes.POINTER(ctypes.c_void_p)] * 8),
     'cfem_apply_reduced': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    'cfem_set_peers': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32,
+                                      ctypes.c_int32,
+                                      ctypes.POINTER(ctypes.c_void_p),
+                                      ctypes.POINTER(ctypes.c_void_p)]),
+    'cfem_peer_layout': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32,
+                                        _c_int64_p, _c_int64_p]),
     'cfem_synchronize': (ctypes.c_int, [ctypes.c_void_p]),
     'cfem_event_record': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     'cfem_event_elapsed_ms': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32,
@@ -360,6 +366,21 @@ class Handle:
         self._check(self.lib.cfem_device_ptrs(
             self._ptr, *[ctypes.byref(p) for p in ptrs]))
         return {n: p.value for n, p in zip(names, ptrs)}
+
+    def peer_layout(self, world):
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self.lib.cfem_peer_layout(self._ptr, int(world),
+                                              ctypes.byref(a),
+                                              ctypes.byref(b)))
+        return a.value, b.value
+
+    def set_peers(self, rank, world, inbox_ptrs, flag_ptrs):
+        """Enable the in-kernel reduction over peer memory."""
+        n = max(1, len(inbox_ptrs))
+        ia = (ctypes.c_void_p * n)(*[int(p) for p in inbox_ptrs])
+        fa = (ctypes.c_void_p * n)(*[int(p) for p in flag_ptrs])
+        self._check(self.lib.cfem_set_peers(self._ptr, int(rank), int(world),
+                                            ia, fa))
 
     def apply_reduced(self, dev_ptr):
         self._check(self.lib.cfem_apply_reduced(self._ptr, int(dev_ptr)))

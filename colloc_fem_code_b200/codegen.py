@@ -634,6 +634,9 @@ class Generator:
             w += undefs
         w.append(f'    for (int r = 0; r < {R}; ++r) '
                  f'a.reduce[b * {R} + r] = tot[r];')
+        w.append('    // time-sharded run: exchange the partial sums with the peer '
+                 'GPUs through NVLink-mapped memory, inside this kernel')
+        w.append(f'    if (a.peer_world > 1) cfem::peer_allreduce<{R}>(a, b, tot);')
         w.append(f'    if (mask & {F}u) a.f[b] = tot[0];')
         w.append(f'    if (mask & {GRAD}u) {{')
         for i, s in enumerate(self.slots[1:], start=1):

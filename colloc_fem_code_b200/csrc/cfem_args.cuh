@@ -7,6 +7,8 @@
 
 namespace cfem {
 
+constexpr int kMaxPeers = 16;
+
 template <int N> struct AtLeastOne { static constexpr int value = N > 0 ? N : 1; };
 
 // Kernel argument block: everything is resolved on the host at cfem_create().
@@ -33,6 +35,11 @@ struct KArgs {
     double*       gpartials;    // [batch][ngroups][nreduce]
     unsigned int* group_count;  // [batch][ngroups] CTAs retired per group
     unsigned int* done_count;   // [batch] groups retired per problem
+    // fused cross-GPU reduction over peer memory (time-sharded runs)
+    int                 peer_rank, peer_world;      // world <= 1: disabled
+    unsigned long long  peer_epoch;                 // launch counter, > 0
+    double*             peer_inbox[kMaxPeers];      // rank p's inbox  [2][world][batch*nreduce]
+    unsigned long long* peer_flag[kMaxPeers];       // rank p's flags  [2][world]
     double* reduce;         // [batch][nreduce]
     long long var_off[AtLeastOne<gen::kNumVars>::value];
     long long var_rows[AtLeastOne<gen::kNumVars>::value];

@@ -337,4 +337,60 @@ __device__ __forceinline__ bool tree_reduce(const KArgs& a, long long b,
     return last_block_done(a.done_count + b, (unsigned)a.ngroups, tid);
 }
 
+// ---------------------------------------------------------------------------
+// fused cross-GPU reduction (time-sharded trajectories)
+// ---------------------------------------------------------------------------
+// Every rank's kernel ends with the same hand-shake, executed by thread 0 of
+// the CTA that finalises the rank's own sums (`tot`, R doubles per problem):
+//   1. store `tot` into slot [parity][my rank] of EVERY rank's inbox (peer
+//      stores through NVLink / NVSwitch-mapped memory);
+//   2. system-scope release store of the launch epoch into the matching flag;
+//   3. spin (acquire loads) until all `world` flags of the own inbox carry the
+//      epoch, then sum the inbox rows IN RANK ORDER -- every rank computes the
+//      same bits -- and continue with the global sums.
+// No NCCL launch, no second kernel, no host round trip: the collective costs
+// two NVLink latencies.  Inboxes are double-buffered by epoch parity: a rank
+// can be at most one launch ahead of the slowest rank (it needs that rank's
+// flag of the current epoch to proceed), so two halves never collide.  All
+// ranks must issue the same sequence of launches (they do: lock-step shards).
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int R>
+__device__ __forceinline__ void peer_allreduce(const KArgs& a, long long b, double (&tot)[R])
+{
+    const int W = a.peer_world, me = a.peer_rank;
+    const unsigned long long epoch = a.peer_epoch;
+    const int half = (int)(epoch & 1ull);
+    const long long nb = (long long)gridDim.y;              // problems per launch
+    const long long row = ((long long)half * W + me) * nb * R + b * R;
+    for (int p = 0; p < W; ++p) {
+        double* dst = a.peer_inbox[p] + row;
+#pragma unroll
+        for (int r = 0; r < R; ++r) __stcg(dst + r, tot[r]);
+    }
+    __threadfence_system();
+    // one flag per (parity, rank, problem) would be needed for batches; a
+    // time-sharded problem has batch == 1, enforced on the host
+    for (int p = 0; p < W; ++p) st_release_sys(a.peer_flag[p] + half * W + me, epoch);
+    const unsigned long long* myflag = a.peer_flag[me] + half * W;
+    for (int p = 0; p < W; ++p)
+        while (ld_acquire_sys(myflag + p) < epoch) { __nanosleep(64); }
+    const double* in = a.peer_inbox[me] + (long long)half * W * nb * R + b * R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) tot[r] = 0.0;
+    for (int p = 0; p < W; ++p) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) tot[r] += __ldcv(in + (long long)p * nb * R + r);
+    }
+}
+
 }  // namespace cfem

@@ -419,6 +419,7 @@ int cfem_eval(cfem_problem* p, uint32_t what)
         p->kev_valid = true;
     }
     p->launches += 1;
+    if (p->k.peer_world > 1 && (mask & (CFEM_F | CFEM_GRAD))) p->k.peer_epoch += 1;
     if (params) CFEM_CUDA(p, cudaStreamWaitEvent(p->stream, p->ev_join, 0));
     p->valid |= mask;
     return CFEM_OK;
@@ -490,6 +491,36 @@ int cfem_device_ptrs(cfem_problem* p, double** dvec, double** lambda, double** f
     if (jac) *jac = p->k.jac;
     if (hess) *hess = p->k.hess;
     if (reduce) *reduce = p->k.reduce;
+    return CFEM_OK;
+}
+
+int cfem_set_peers(cfem_problem* p, int32_t rank, int32_t world,
+                   void* const* inbox_ptrs, void* const* flag_ptrs)
+{
+    if (!p) return CFEM_EINVAL;
+    if (world <= 1) { p->k.peer_world = 0; return CFEM_OK; }
+    if (rank < 0 || rank >= world || world > cfem::kMaxPeers || !inbox_ptrs || !flag_ptrs)
+        return cfem::fail(p, CFEM_EINVAL, "cfem_set_peers: bad rank/world/pointers", cudaSuccess);
+    if (p->batch != 1)
+        return cfem::fail(p, CFEM_EINVAL, "cfem_set_peers: time-sharding needs batch == 1", cudaSuccess);
+    for (int i = 0; i < world; ++i) {
+        if (!inbox_ptrs[i] || !flag_ptrs[i])
+            return cfem::fail(p, CFEM_EINVAL, "cfem_set_peers: null peer pointer", cudaSuccess);
+        p->k.peer_inbox[i] = (double*)inbox_ptrs[i];
+        p->k.peer_flag[i] = (unsigned long long*)flag_ptrs[i];
+    }
+    p->k.peer_rank = rank;
+    p->k.peer_world = world;
+    p->k.peer_epoch = 1;        // flags start at 0
+    return CFEM_OK;
+}
+
+int cfem_peer_layout(const cfem_problem* p, int32_t world, int64_t* inbox_doubles,
+                     int64_t* flag_words)
+{
+    if (!p || world < 1) return CFEM_EINVAL;
+    if (inbox_doubles) *inbox_doubles = 2ll * world * p->batch * gen::kNumReduce;
+    if (flag_words) *flag_words = 2ll * world;
     return CFEM_OK;
 }
 

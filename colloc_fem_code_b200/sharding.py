@@ -194,6 +194,33 @@ class ShardedEvaluator:
             raise backend.CfemError(f'shard layout mismatch: {got} vs {want}')
         self.n_reduce = len(self.lib.model['reduce'])
 
+    def enable_peer_reduce(self, group=None):
+        """Switch from ``all_reduce`` + ``cfem_apply_reduced`` to the fused
+        in-kernel exchange over NVLink peer memory (``cfem_set_peers``).
+
+        PyTorch is only the plumbing here: a symmetric-memory allocation
+        (``torch.distributed._symmetric_memory``) gives every rank a device
+        pointer to every other rank's inbox; the exchange itself is done by
+        the last CTA of the per-sample kernel.
+        """
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = group or dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n_inbox, n_flag = self.handle.peer_layout(world)
+        buf = symm.empty(n_inbox + n_flag, dtype=torch.float64,
+                         device=torch.device('cuda', torch.cuda.current_device()))
+        buf.zero_()
+        hdl = symm.rendezvous(buf, group)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        torch.cuda.synchronize()
+        dist.barrier(group)             # every inbox is zeroed before any store
+        self.handle.set_peers(rank, world, ptrs,
+                              [p + 8 * n_inbox for p in ptrs])
+        self._peer = (buf, hdl)         # keep the mapping alive
+        return True
+
     def set_point(self, dvec, obj_factor, lam):
         self.handle.set_dvec(self.shard.local_dvec(dvec))
         self.handle.set_multipliers(obj_factor,

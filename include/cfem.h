@@ -145,6 +145,17 @@ int          cfem_device_ptrs(cfem_problem* p, double** dvec, double** lambda,
 /* Time-sharded runs: add the all-reduced [batch][n_reduce] vector back into f
  * and the gradient (device pointer, same stream). */
 int          cfem_apply_reduced(cfem_problem* p, const double* reduce_dev);
+/* Fused alternative to all-reduce + cfem_apply_reduced: every rank's kernel
+ * exchanges its [n_reduce] partial sums with the peers through NVLink-mapped
+ * memory and finishes with the global objective / parameter gradient itself.
+ * inbox_ptrs[r] / flag_ptrs[r]: rank r's inbox (cfem_peer_layout doubles) and
+ * flag words (uint64), zero-initialised, mapped into THIS process (CUDA IPC /
+ * symmetric memory); entry `rank` is the local one.  All ranks must then issue
+ * the same sequence of cfem_eval calls.  world <= 1 switches it off. */
+int          cfem_set_peers(cfem_problem* p, int32_t rank, int32_t world,
+                            void* const* inbox_ptrs, void* const* flag_ptrs);
+int          cfem_peer_layout(const cfem_problem* p, int32_t world,
+                              int64_t* inbox_doubles, int64_t* flag_words);
 int          cfem_synchronize(cfem_problem* p);
 
 /* ---- measurement helpers --------------------------------------------------- */

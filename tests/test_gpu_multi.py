@@ -1,0 +1,101 @@
+"""Two-GPU run of the time-sharded evaluation (skipped with fewer GPUs):
+results assembled from two ranks -- with the fused in-kernel peer-memory
+reduction and with NCCL all_reduce -- equal the single-GPU evaluation."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _rank_main(rank, world, port, mode, out):
+    import torch
+    import torch.distributed as dist
+    from colloc_fem_code_b200 import backend, families, sharding, synthetic
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    try:
+        nx, nu, ny, N = 2, 1, 2, 20001
+        exp = synthetic.experiment(5, N, nx, nu, ny)
+        p = families.make_problem('ml', exp['y'], exp['u'], nx)
+        dvec, lam, sigma = synthetic.evaluation_point(p, exp)
+        ev = sharding.ShardedEvaluator(p, rank, world, device=rank)
+        h = ev.handle
+        stream = torch.cuda.Stream(device=rank)
+        torch.cuda.set_stream(stream)
+        h.set_stream(stream.cuda_stream)
+        if mode == 'peer':
+            ev.enable_peer_reduce()
+        res = {}
+        for rep in range(3):                 # several epochs of the hand-shake
+            ev.set_point(dvec + 1e-3 * rep, sigma, lam)
+            h.eval(backend.ALL)
+            if mode == 'nccl':
+                ptr = h.device_ptrs()['reduce']
+
+                class Arr:
+                    __cuda_array_interface__ = {
+                        'shape': (ev.n_reduce,), 'typestr': '<f8',
+                        'data': (ptr, False), 'version': 2}
+                red = torch.as_tensor(Arr(), device=f'cuda:{rank}')
+                dist.all_reduce(red)
+                h.apply_reduced(ptr)
+            res = {k: h.fetch(b) for k, b in (('f', 1), ('grad', 2), ('g', 4),
+                                              ('jac', 8), ('hess', 16))}
+        parts = {k: ev.shard.scatter(k, res[k],
+                                     np.zeros(ev.shard.global_size(k)))
+                 for k in ('grad', 'g', 'jac', 'hess')}
+        parts['f'] = float(res['f'][0])
+        gathered = [None] * world
+        dist.gather_object(parts, gathered if rank == 0 else None, dst=0)
+        if rank == 0:
+            d = dvec + 1e-3 * 2
+            ref = {'f': p.obj(d), 'grad': p.obj_grad(d), 'g': p.constr(d),
+                   'jac': p.constr_jac_val(d),
+                   'hess': p.lag_hess_val(d, sigma, lam)}
+            assert gathered[0]['f'] == gathered[1]['f']     # same bits
+            np.testing.assert_allclose(gathered[0]['f'], ref['f'], rtol=1e-13)
+            for k in ('g', 'jac', 'hess'):
+                full = sum(g[k] for g in gathered)
+                np.testing.assert_array_equal(full, ref[k], err_msg=k)
+            full = sum(g['grad'] for g in gathered)
+            np.testing.assert_allclose(full, ref['grad'], rtol=1e-13,
+                                       atol=1e-300)
+            out.put('ok')
+    except Exception as exc:            # pragma: no cover
+        out.put(f'rank {rank}: {exc!r}')
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('mode', ['peer', 'nccl'])
+def test_two_gpu_sharded_equals_single(mode):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, mode, out))
+             for r in range(2)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(600)
+    msg = out.get(timeout=10)
+    assert msg == 'ok', msg
+    assert all(pr.exitcode == 0 for pr in procs)
