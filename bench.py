@@ -136,7 +136,7 @@ class CudaArray:
             'version': 2}
 
 
-def run_reference(args):
+def run_reference(args, out):
     """The reference's CPU evaluation (the NumPy oracle port: the reference's
     own stack -- ceacoest / sym2num -- is not installable), same workload."""
     rank = int(os.environ.get('RANK', 0))
@@ -169,7 +169,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = args.steps / dt
     sample = f'full workload: N={N} samples per step, {args.steps} steps'
-    print(json.dumps({
+    out.emit(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True,
@@ -186,7 +186,8 @@ def run_reference(args):
 
 def workload_config(world, reduce_mode='none'):
     nx, nu, ny = DIMS
-    how = {'peer': 'objective + parameter gradient reduced inside the kernel '
+    how = {'skip': 'NO reduction (debug only: results incomplete)',
+           'peer': 'objective + parameter gradient reduced inside the kernel '
                    'over NVLink peer memory (no NCCL call on the path)',
            'nccl': 'NCCL allreduce of objective + parameter gradient',
            'none': ''}[reduce_mode]
@@ -231,7 +232,7 @@ def cpu_baseline():
             'host_cores_available': os.cpu_count()}
 
 
-def run_ours(args):
+def run_ours(args, out):
     import torch
     import torch.distributed as dist
     from colloc_fem_code_b200 import backend, families, sharding, synthetic
@@ -319,10 +320,9 @@ def run_ours(args):
         h.flush_l2(FLUSH_BYTES)
         starts[i].record()
         device_step()
-        stops[i].record()
-        if (i & 7) == 7 or i == args.steps - 1:
-            kernel_ms.append(h.last_sample_kernel_ms())
+        stops[i].record()        # no host synchronisation inside the loop
     sync_all()
+    kernel_ms = h.sample_kernel_ms_history(min(args.steps, 64))
     wall = time.perf_counter() - t_wall
     launches = h.launch_count - launches0
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
@@ -405,7 +405,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline()
-        print(json.dumps(line))
+        out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -421,6 +421,26 @@ def ncu_traffic():
         return None
 
 
+class OneLineStdout:
+    """Everything libraries print to fd 1 during the run (e.g. NCCL's version
+    banner) goes to stderr; only the final JSON line reaches stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self._saved, (line + '\n').encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -430,10 +450,11 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.impl == 'reference':
-        run_reference(args)
-    else:
-        run_ours(args)
+    with OneLineStdout() as out:
+        if args.impl == 'reference':
+            run_reference(args, out)
+        else:
+            run_ours(args, out)
 
 
 if __name__ == '__main__':

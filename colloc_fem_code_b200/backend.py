@@ -95,6 +95,10 @@ ABI = {
     'cfem_last_sample_kernel_ms': (ctypes.c_int,
                                    [ctypes.c_void_p,
                                     ctypes.POINTER(ctypes.c_float)]),
+    'cfem_sample_kernel_ms_history': (ctypes.c_int,
+                                      [ctypes.c_void_p,
+                                       ctypes.POINTER(ctypes.c_float),
+                                       ctypes.c_int32]),
     'cfem_launch_count': (ctypes.c_int64, [ctypes.c_void_p]),
     'cfem_flush_l2': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
     'cfem_host_alloc': (ctypes.c_void_p, [ctypes.c_size_t]),
@@ -403,6 +407,12 @@ class Handle:
         self._check(self.lib.cfem_last_sample_kernel_ms(self._ptr,
                                                         ctypes.byref(ms)))
         return ms.value
+
+    def sample_kernel_ms_history(self, n):
+        n = int(min(n, 64))
+        arr = (ctypes.c_float * n)()
+        self._check(self.lib.cfem_sample_kernel_ms_history(self._ptr, arr, n))
+        return list(arr)
 
     @property
     def launch_count(self):

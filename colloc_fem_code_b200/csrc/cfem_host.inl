@@ -35,9 +35,10 @@ struct cfem_problem {
     bool          have_lam = false;
     unsigned      valid = 0;
     cudaEvent_t   ev[16] = {};
-    cudaEvent_t   kev[2] = {};          // around the per-sample kernel
+    static constexpr int kTimingRing = 64;
+    cudaEvent_t   kev[2 * kTimingRing] = {};    // pairs around the per-sample kernel
     bool          timing = false;
-    bool          kev_valid = false;
+    long long     kev_count = 0;        // timed launches so far
     long long     launches = 0;
     void*         flush_buf = nullptr;
     size_t        flush_bytes = 0;
@@ -412,11 +413,12 @@ int cfem_eval(cfem_problem* p, uint32_t what)
         CFEM_CUDA(p, cudaEventRecord(p->ev_join, p->aux_stream));
         p->launches += 1;
     }
-    if (p->timing) CFEM_CUDA(p, cudaEventRecord(p->kev[0], p->stream));
+    const int slot = (int)(p->kev_count % cfem_problem::kTimingRing);
+    if (p->timing) CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot], p->stream));
     CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->stream, p->k));
     if (p->timing) {
-        CFEM_CUDA(p, cudaEventRecord(p->kev[1], p->stream));
-        p->kev_valid = true;
+        CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot + 1], p->stream));
+        p->kev_count += 1;
     }
     p->launches += 1;
     if (p->k.peer_world > 1 && (mask & (CFEM_F | CFEM_GRAD))) p->k.peer_epoch += 1;
@@ -563,19 +565,27 @@ int cfem_set_kernel_timing(cfem_problem* p, int32_t enabled)
 {
     if (!p) return CFEM_EINVAL;
     p->timing = enabled != 0;
-    p->kev_valid = false;
+    p->kev_count = 0;
+    return CFEM_OK;
+}
+
+int cfem_sample_kernel_ms_history(cfem_problem* p, float* ms, int32_t n)
+{
+    if (!p || !ms || n < 1) return CFEM_EINVAL;
+    if (p->kev_count < n || n > cfem_problem::kTimingRing)
+        return cfem::fail(p, CFEM_ESTATE, "cfem_sample_kernel_ms_history: not that many timed launches", cudaSuccess);
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    for (int i = 0; i < n; ++i) {           // ms[0] = oldest of the last n
+        const int slot = (int)((p->kev_count - n + i) % cfem_problem::kTimingRing);
+        CFEM_CUDA(p, cudaEventSynchronize(p->kev[2 * slot + 1]));
+        CFEM_CUDA(p, cudaEventElapsedTime(ms + i, p->kev[2 * slot], p->kev[2 * slot + 1]));
+    }
     return CFEM_OK;
 }
 
 int cfem_last_sample_kernel_ms(cfem_problem* p, float* ms)
 {
-    if (!p || !ms) return CFEM_EINVAL;
-    if (!p->kev_valid)
-        return cfem::fail(p, CFEM_ESTATE, "cfem_last_sample_kernel_ms: no timed launch", cudaSuccess);
-    CFEM_CUDA(p, cudaSetDevice(p->device));
-    CFEM_CUDA(p, cudaEventSynchronize(p->kev[1]));
-    CFEM_CUDA(p, cudaEventElapsedTime(ms, p->kev[0], p->kev[1]));
-    return CFEM_OK;
+    return cfem_sample_kernel_ms_history(p, ms, 1);
 }
 
 int64_t cfem_launch_count(const cfem_problem* p) { return p ? p->launches : -1; }

@@ -168,6 +168,9 @@ int          cfem_event_elapsed_ms(cfem_problem* p, int32_t start_slot,
  * cfem_last_sample_kernel_ms returns the duration of the latest such launch. */
 int          cfem_set_kernel_timing(cfem_problem* p, int32_t enabled);
 int          cfem_last_sample_kernel_ms(cfem_problem* p, float* ms);
+/* Durations of the last n (<= 64) timed launches, oldest first: lets a timed
+ * loop run without any host synchronisation inside it. */
+int          cfem_sample_kernel_ms_history(cfem_problem* p, float* ms, int32_t n);
 /* Number of kernels this handle has launched so far. */
 int64_t      cfem_launch_count(const cfem_problem* p);
 /* Write `bytes` of zeros to a scratch buffer (L2 flush between timed iterations). */
