@@ -127,6 +127,31 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this process to the CPUs of the GPU's NUMA node so that the pinned
+    host buffers (first touch) and the DMA engines sit on the same socket."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device)
+        bus = f'{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:' \
+              f'{props.pci_device_id:02x}.0'
+        with open(f'/sys/bus/pci/devices/{bus}/numa_node') as fh:
+            node = int(fh.read())
+        if node < 0:
+            return None
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as fh:
+            cpus = set()
+            for part in fh.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 class CudaArray:
     """Zero-copy torch view of a device buffer owned by a cfem handle."""
 
@@ -243,6 +268,7 @@ def run_ours(args, out):
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device(
@@ -380,6 +406,7 @@ def run_ours(args, out):
             'data': 'synthetic',
             'config': workload_config(world, reduce_mode),
             'samples_per_s': value * N_PER_GPU,
+            'numa_node': numa_node,
             'gpu_launches': int(launches),
             'wall_s_timed_region': wall,
             'clocks': clocks,
