@@ -151,15 +151,34 @@ class GpuEvaluator(Evaluator):
         return (float(b.f[0]), b.grad.copy(), b.g.copy(), b.jac.copy(),
                 b.hess.copy())
 
-    # IPOPT-shaped single callbacks (used by IpoptSolver)
+    # IPOPT-shaped single callbacks (used by IpoptSolver).  IPOPT asks for f
+    # and g at every trial point and for grad f, the Jacobian and the Hessian
+    # at accepted points, one callback at a time; the fused kernels serve a
+    # whole group per launch and `new_x` tells when the groups go stale:
+    #   f or g       -> one launch of mask F|G
+    #   grad or Jac  -> one launch of mask F|GRAD|G|JAC
+    #   Hessian      -> one launch of mask HESS (multipliers change per call)
+    _GROUP = {backend.F: backend.F | backend.G,
+              backend.G: backend.F | backend.G,
+              backend.GRAD: backend.F | backend.GRAD | backend.G | backend.JAC,
+              backend.JAC: backend.F | backend.GRAD | backend.G | backend.JAC,
+              backend.HESS: backend.HESS}
+
     def ipopt_eval(self, which, x, new_x, out, sigma=None, lam=None):
         t0 = time.perf_counter()
-        if new_x:
+        if new_x or not getattr(self, '_have_x', False):
             self._set_x(x)
+            self._have_x = True
+            self._fresh = 0
         if which == backend.HESS:
             self.buf.lam[:] = lam
             self.h.set_multipliers(sigma, self.buf.lam)
-        self.h.eval(which)
+            self._fresh &= ~backend.HESS
+        if not (self._fresh & which):
+            mask = self._GROUP[which]
+            self.h.eval(mask)
+            self._fresh |= mask
+            self.kernel_groups = getattr(self, 'kernel_groups', 0) + 1
         self.h.fetch(which, out)
         self.seconds += time.perf_counter() - t0
         self.calls += 1

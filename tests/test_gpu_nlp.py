@@ -70,3 +70,31 @@ def test_batch_fitter_matches_single_fits():
         assert infos['iterations'] == infob['iterations']
         np.testing.assert_allclose(xb, xs, rtol=1e-9, atol=1e-11)
     assert bf.launches < sum(i['callback_calls'] for _, i in singles)
+
+
+def test_ipopt_callback_grouping_against_fake_ipopt(tmp_path):
+    """The ctypes IPOPT binding driven by the CUDA evaluator: the fake
+    libipopt (tests/fake_ipopt.c) calls every callback once; values must be
+    the oracle's and the five callbacks must cost three kernel groups."""
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    lib = str(tmp_path / 'libipopt_fake.so')
+    subprocess.run(['gcc', '-shared', '-fPIC', '-O1', '-o', lib,
+                    os.path.join(here, 'fake_ipopt.c')], check=True)
+    exp, p, o, dec0, (db, cb, scaling) = _case(3, 300)
+    ev = nlp.GpuEvaluator(p)
+    s = nlp.IpoptSolver(ev, db, cb, libpath=lib)
+    s.set_scaling(*scaling)
+    x, info = s.solve(dec0)
+    assert info['status'] == 0 and info['last_error'] is None
+    lam = 0.5 + 0.01 * np.arange(o.ncons)
+    np.testing.assert_allclose(info['obj'], o.obj(dec0), rtol=1e-12)
+    np.testing.assert_allclose(info['g'], o.constr(dec0), atol=1e-12)
+    L = info['mult_x_L']
+    np.testing.assert_allclose(L[0], o.constr_jac_val(dec0).sum(), rtol=1e-11)
+    np.testing.assert_allclose(L[1], o.lag_hess_val(dec0, 0.75, lam).sum(),
+                               rtol=1e-11)
+    np.testing.assert_allclose(L[2], o.obj_grad(dec0).sum(), rtol=1e-11)
+    assert ev.kernel_groups == 3
+    s.close()
