@@ -192,3 +192,80 @@ def test_full_size_million_samples(dims):
     hess1 = p.lag_hess_val(dvec, sigma, lam)
     hess2 = p.lag_hess_val(dvec, 2 * sigma, 2 * lam)
     np.testing.assert_allclose(hess2, 2 * hess1, rtol=1e-15)
+
+
+@pytest.mark.parametrize('kind,dims,N,world', [
+    ('innovation', (2, 1, 2), 1001, 2), ('ml_balanced', (2, 1, 2), 777, 3),
+    ('ndisc_zoh', (4, 2, 7), 301, 2), ('innovation', (5, 3, 3), 4099, 4)])
+def test_time_shards_on_one_gpu(kind, dims, N, world):
+    """The halo = 1 handles of a time-sharded trajectory, evaluated one after
+    the other on ONE GPU: the assembled results equal the unsharded CUDA
+    evaluation bit for bit (g, Jacobian, Hessian, per-sample gradient) and the
+    summed [f, d f/d params] partials equal it to rounding."""
+    from colloc_fem_code_b200 import sharding
+    nx, nu, ny = dims
+    exp = synthetic.experiment(N, N, nx, nu, ny)
+    p = families.make_problem(kind, exp['y'], exp['u'], nx, dt=0.05)
+    dvec, lam, sigma = synthetic.evaluation_point(p, exp, seed=1)
+    ref = cuda_callbacks(p, dvec, sigma, lam)
+    full = {k: np.zeros_like(ref[k]) for k in ('grad', 'g', 'jac', 'hess')}
+    red_sum = None
+    for rank in range(world):
+        ev = sharding.ShardedEvaluator(p, rank, world)
+        ev.set_point(dvec, sigma, lam)
+        h = ev.handle
+        h.eval(backend.ALL)
+        loc = {k: h.fetch(b) for k, b in (('grad', 2), ('g', 4), ('jac', 8),
+                                          ('hess', 16))}
+        for k in full:
+            ev.shard.scatter(k, loc[k], full[k])
+        import ctypes
+        red = np.empty(ev.n_reduce)
+        # the [n_reduce] partial of this shard (device buffer -> host)
+        import torch
+        ptr = h.device_ptrs()['reduce']
+
+        class Arr:
+            __cuda_array_interface__ = {'shape': (ev.n_reduce,),
+                                        'typestr': '<f8',
+                                        'data': (ptr, False), 'version': 2}
+        red[:] = torch.as_tensor(Arr(), device='cuda:0').cpu().numpy()
+        red_sum = red if red_sum is None else red_sum + red
+        h.close()
+    for k in ('g', 'jac', 'hess'):
+        np.testing.assert_array_equal(full[k], ref[k], err_msg=k)
+    np.testing.assert_allclose(red_sum[0], ref['f'], rtol=1e-13)
+    # parameter entries of the gradient come from the summed partials
+    slots = ev.lib.model['reduce'][1:]
+    st = p.structure
+    for (var, flat), val in zip(slots, red_sum[1:]):
+        idx = p.decision[st.var_names[var]].offset + flat
+        full['grad'][idx] = val
+    np.testing.assert_allclose(full['grad'], ref['grad'], rtol=1e-13,
+                               atol=1e-300)
+
+
+def test_batched_problems_match_single_problem_evaluation():
+    """cfem_create(batch = B): blockIdx.y = problem (Monte-Carlo batches)."""
+    nx, nu, ny, N, B = 5, 3, 3, 250, 5
+    cases = []
+    for b in range(B):
+        exp = synthetic.experiment(100 + b, N, nx, nu, ny)
+        p = families.make_problem('ml_balanced', exp['y'], exp['u'], nx)
+        cases.append((p,) + synthetic.evaluation_point(p, exp, seed=b))
+    p0 = cases[0][0]
+    st = p0.structure
+    lib = backend.Library.for_structure(st)
+    data = [np.stack([c[0].structure.data[i]['source'] for c in cases])
+            for i in range(len(st.data))]
+    h = backend.Handle(lib, N, data, st.scalar_values, batch=B)
+    h.set_dvec(np.stack([c[1] for c in cases]))
+    h.set_multipliers(0.9, np.stack([c[2] for c in cases]))
+    h.eval(backend.ALL)
+    out = {k: h.fetch(b) for k, b in (('f', 1), ('grad', 2), ('g', 4),
+                                      ('jac', 8), ('hess', 16))}
+    for b, (p, dvec, lam, _) in enumerate(cases):
+        one = p.backend.eval_all(dvec, 0.9, lam)
+        for k, v in zip(('f', 'grad', 'g', 'jac', 'hess'), one):
+            np.testing.assert_array_equal(np.ravel(out[k][b]), np.ravel(v),
+                                          err_msg=f'{k} problem {b}')
