@@ -10,6 +10,7 @@ write them (cooperative multiple inheritance, as in the reference):
 ``ml_zoh``       attas_sp_ml_zoh.py:49-54
 ``ndisc_zoh``    attas_sp_ml_ndisc.py:49-54
 ``ml_balanced``  mc_blackbox_cfem.py:25-30
+``trapezoid``    extension: trapezoidal collocation, no reference class
 ===============  =====================================================
 """
 
@@ -25,6 +26,8 @@ COMPOSITIONS = {
                   ('DiscretizedNoiseProblem', 'ZOHDynamicsProblem')),
     'ml_balanced': (('MaximumLikelihoodDTModel', 'BalancedDTModel'),
                     ('MaximumLikelihoodDTProblem', 'BalancedDTProblem')),
+    # extension without reference counterpart (trapezoidal collocation)
+    'trapezoid': (('TrapezoidalCTModel',), ('TrapezoidalCTProblem',)),
 }
 
 _model_classes = {}

@@ -279,3 +279,55 @@ class DiscretizedNoiseModel(MaximumLikelihoodDTModel):
                 total = total + (term if j == k else term + term.T)
         resid = total - sQ @ sQ.T
         return [resid[ij] for ij in tril_ind(self.nx)]
+
+
+class TrapezoidalCTModel(symoptim.Model):
+    """EXTENSION -- no reference counterpart at the reference's HEAD.
+
+    Continuous-time innovation-form predictor ``dx/dt = Ac x + Bc u + Lc en``
+    collocated with the trapezoidal rule (BASELINE.json names trapezoidal
+    defects; the reference only has the discrete-time defect of
+    symfem.py:50-53 and the parameter-only ZOH constraint of :193-202):
+
+        x[k+1] - x[k] - dt/2 (f[k] + f[k+1]) = 0,
+        f[k] = Ac x[k] + Bc u[k] + Lc en[k]
+
+    a two-sample stencil in ``x``, ``en`` and ``u``.  ``innovation`` and
+    ``loglikelihood`` are the reference's (symfem.py:55-65).
+    """
+
+    def __init__(self, nx, nu, ny):
+        super().__init__()
+        self.nx, self.nu, self.ny = nx, nu, ny
+        v = self.variables
+        for name, n in (('x', nx), ('en', ny), ('xnext', nx), ('xprev', nx),
+                        ('enprev', ny), ('ennext', ny), ('ybias', ny)):
+            v[name] = _vector(name, n)
+        v['Ac'] = _matrix('Ac', nx, nx)
+        v['Bc'] = _matrix('Bc', nx, nu)
+        v['C'] = _matrix('C', ny, nx)
+        v['D'] = _matrix('D', ny, nu)
+        v['Lc'] = _matrix('Lc', nx, ny)
+        v['sRp_tril'] = _tril('sRp', ny)
+        self.decision.update(name for name in v if name != 'self')
+        for name, n in (('u', nu), ('y', ny), ('uprev', nu), ('unext', nu)):
+            v[name] = _vector(name, n)
+        v['dt'] = 'dt'
+        self.add_constraint('trapezoid')
+        self.add_constraint('innovation')
+        self.add_objective('loglikelihood')
+
+    def trapezoid(self, xnext, xprev, unext, uprev, ennext, enprev, Ac, Bc,
+                  Lc, dt):
+        """Trapezoidal collocation defect of the continuous-time predictor."""
+        fprev = Ac @ xprev + Bc @ uprev + Lc @ enprev
+        fnext = Ac @ xnext + Bc @ unext + Lc @ ennext
+        return xnext - xprev - 0.5 * dt * (fprev + fnext)
+
+    innovation = InnovationDTModel.innovation
+    loglikelihood = InnovationDTModel.loglikelihood
+
+    @property
+    def generate_assignments(self):
+        return {'nx': self.nx, 'nu': self.nu, 'ny': self.ny,
+                'nty': len(self.variables['sRp_tril'])}

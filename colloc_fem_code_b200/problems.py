@@ -129,3 +129,42 @@ class DiscretizedNoiseProblem(MaximumLikelihoodDTProblem):
 
     def variables(self, dvec):
         return _with_sample_time(self, super().variables(dvec))
+
+
+class TrapezoidalCTProblem(optim.Problem):
+    """EXTENSION -- no reference counterpart (see models.TrapezoidalCTModel).
+    Layout in the manner of fem.py:36-57: parameters, then the ``x`` and
+    ``en`` slabs; ``xprev/xnext`` and ``enprev/ennext`` are the two one-sample
+    shifted views of the slabs, ``uprev/unext`` those of the inputs."""
+
+    def __init__(self, model, y, u):
+        super().__init__()
+        self.model = model
+        self.y = np.asarray(y)
+        self.u = np.asarray(u)
+        self.uprev, self.unext = self.u[:-1], self.u[1:]
+        self.N = N = len(self.y)
+        nx, nu, ny = model.nx, model.nu, model.ny
+        if self.y.shape != (N, ny) or self.u.shape != (N, nu) or N <= 1:
+            raise AssertionError('y must be (N, ny), u (N, nu), N > 1')
+        for name, shape in (('ybias', ny), ('sRp_tril', model.nty),
+                            ('Ac', (nx, nx)), ('Bc', (nx, nu)),
+                            ('C', (ny, nx)), ('D', (ny, nu)),
+                            ('Lc', (nx, ny))):
+            self.add_decision(name, shape)
+        x = self.add_decision('x', (N, nx))
+        en = self.add_decision('en', (N, ny))
+        for name, shape, offset in (
+                ('xprev', (N - 1, nx), x.offset),
+                ('xnext', (N - 1, nx), x.offset + nx),
+                ('enprev', (N - 1, ny), en.offset),
+                ('ennext', (N - 1, ny), en.offset + ny)):
+            self.add_dependent_variable(name, optim.Decision(shape, offset))
+        self.add_objective(model.loglikelihood, N)
+        self.add_constraint(model.trapezoid, (N - 1, nx))
+        self.add_constraint(model.innovation, (N, ny))
+
+    def variables(self, dvec):
+        data = {'y': self.y, 'u': self.u, 'uprev': self.uprev,
+                'unext': self.unext, 'dt': self.model.dt}
+        return {**data, **super().variables(dvec)}

@@ -372,6 +372,81 @@ class FilterErrorProblem(engine.Problem):
         return out
 
 
+class TrapezoidalModel(engine.Model):
+    """EXTENSION without reference counterpart: continuous-time predictor
+    dx/dt = Ac x + Bc u + Lc en collocated with the trapezoidal rule.  The
+    oracle of this family is this independent sympy statement (matrix form;
+    the product states it with NumPy object arrays)."""
+
+    def __init__(self, nx, nu, ny):
+        super().__init__()
+        self.nx, self.nu, self.ny = nx, nu, ny
+        v = self.variables
+        for name, n in (('x', nx), ('en', ny), ('xnext', nx), ('xprev', nx),
+                        ('enprev', ny), ('ennext', ny), ('ybias', ny)):
+            v[name] = _names(name, n)
+        for name, shape in (('Ac', (nx, nx)), ('Bc', (nx, nu)),
+                            ('C', (ny, nx)), ('D', (ny, nu)),
+                            ('Lc', (nx, ny))):
+            v[name] = _names(name, *shape)
+        v['sRp_tril'] = _tril_names('sRp', ny)
+        self.decision |= {k for k in v if k != 'self'}
+        for name, n in (('u', nu), ('y', ny), ('uprev', nu), ('unext', nu)):
+            v[name] = _names(name, n)
+        v['dt'] = 'dt'
+        self.add_constraint('trapezoid')
+        self.add_constraint('innovation')
+        self.add_objective('loglikelihood')
+
+    def trapezoid(self, xnext, xprev, unext, uprev, ennext, enprev, Ac, Bc,
+                  Lc, dt):
+        f0 = _mat(Ac) * _mat(xprev) + _mat(Bc) * _mat(uprev) \
+            + _mat(Lc) * _mat(enprev)
+        f1 = _mat(Ac) * _mat(xnext) + _mat(Bc) * _mat(unext) \
+            + _mat(Lc) * _mat(ennext)
+        return _vec(_mat(xnext) - _mat(xprev)
+                    - sympy.Float(0.5) * dt * (f0 + f1))
+
+    innovation = FilterErrorModel.innovation
+    loglikelihood = FilterErrorModel.loglikelihood
+
+    @property
+    def generate_assignments(self):
+        return {'nx': self.nx, 'nu': self.nu, 'ny': self.ny,
+                'nty': len(self.variables['sRp_tril'])}
+
+
+class TrapezoidalProblem(engine.Problem):
+    def __init__(self, model, y, u):
+        super().__init__()
+        self.model = model
+        self.y = np.asarray(y, dtype=float)
+        self.u = np.asarray(u, dtype=float)
+        N = self.N = len(self.y)
+        nx, nu, ny = model.nx, model.nu, model.ny
+        for name, shape in (('ybias', ny), ('sRp_tril', model.nty),
+                            ('Ac', (nx, nx)), ('Bc', (nx, nu)),
+                            ('C', (ny, nx)), ('D', (ny, nu)),
+                            ('Lc', (nx, ny))):
+            self.add_decision(name, shape)
+        x = self.add_decision('x', (N, nx))
+        en = self.add_decision('en', (N, ny))
+        D = engine.Decision
+        self.add_dependent_variable('xprev', D((N - 1, nx), x.offset))
+        self.add_dependent_variable('xnext', D((N - 1, nx), x.offset + nx))
+        self.add_dependent_variable('enprev', D((N - 1, ny), en.offset))
+        self.add_dependent_variable('ennext', D((N - 1, ny), en.offset + ny))
+        self.add_objective(model.loglikelihood, N)
+        self.add_constraint(model.trapezoid, (N - 1, nx))
+        self.add_constraint(model.innovation, (N, ny))
+
+    def variables(self, dvec):
+        out = {'y': self.y, 'u': self.u, 'uprev': self.u[:-1],
+               'unext': self.u[1:], 'dt': self.model.dt}
+        out.update(super().variables(dvec))
+        return out
+
+
 _model_cache = {}
 
 
@@ -379,7 +454,8 @@ def make_model(kind, nx, nu, ny):
     """Compiled oracle model instance (cached: sympy differentiation is slow)."""
     key = (kind, nx, nu, ny)
     if key not in _model_cache:
-        sym = FilterErrorModel(nx, nu, ny, KINDS[kind])
+        sym = TrapezoidalModel(nx, nu, ny) if kind == 'trapezoid' else \
+            FilterErrorModel(nx, nu, ny, KINDS[kind])
         _model_cache[key] = sym.compile_class()
     return _model_cache[key]()
 
@@ -390,4 +466,7 @@ def make_problem(kind, y, u, nx, dt=None, halo=0):
     model = make_model(kind, nx, u.shape[1], y.shape[1])
     if dt is not None:
         model.dt = dt
+    if kind == 'trapezoid':
+        assert halo == 0
+        return TrapezoidalProblem(model, y, u)
     return FilterErrorProblem(model, y, u, KINDS[kind], halo=halo)

@@ -95,6 +95,9 @@ CASES = [
     ('innovation', (4, 2, 7), 2), ('innovation', (4, 2, 7), 129),
     ('ndisc_zoh', (4, 2, 7), 601), ('innovation', (4, 2, 7), 10000),
     ('innovation', (1, 1, 1), 33), ('innovation', (3, 2, 1), 4097),
+    # extension without reference counterpart: trapezoidal collocation
+    ('trapezoid', (2, 1, 2), 2), ('trapezoid', (2, 1, 2), 1000),
+    ('trapezoid', (3, 2, 2), 4097),
 ]
 
 
@@ -196,7 +199,8 @@ def test_full_size_million_samples(dims):
 
 @pytest.mark.parametrize('kind,dims,N,world', [
     ('innovation', (2, 1, 2), 1001, 2), ('ml_balanced', (2, 1, 2), 777, 3),
-    ('ndisc_zoh', (4, 2, 7), 301, 2), ('innovation', (5, 3, 3), 4099, 4)])
+    ('ndisc_zoh', (4, 2, 7), 301, 2), ('innovation', (5, 3, 3), 4099, 4),
+    ('trapezoid', (3, 2, 2), 1025, 3)])
 def test_time_shards_on_one_gpu(kind, dims, N, world):
     """The halo = 1 handles of a time-sharded trajectory, evaluated one after
     the other on ONE GPU: the assembled results equal the unsharded CUDA
