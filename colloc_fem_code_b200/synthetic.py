@@ -97,10 +97,12 @@ def evaluation_point(problem, exp, seed=0):
     dvec = rng.normal(size=problem.ndec)
     var = problem.variables(dvec)
     for name in ('A', 'B', 'C', 'D'):
-        var[name][...] = exp[name] * (1 + 0.01 * rng.normal(
-            size=exp[name].shape))
+        if name in problem.decision:
+            var[name][...] = exp[name] * (1 + 0.01 * rng.normal(
+                size=exp[name].shape))
     var['ybias'][...] = 0.01 * rng.normal(size=var['ybias'].shape)
-    var['Ln'][...] = 0.1 * rng.normal(size=var['Ln'].shape)
+    if 'Ln' in problem.decision:
+        var['Ln'][...] = 0.1 * rng.normal(size=var['Ln'].shape)
     var['x'][...] = exp['x'] + 0.1 * rng.normal(size=exp['x'].shape)
     for name, spec in problem.decision.items():
         if name.endswith('_tril'):
