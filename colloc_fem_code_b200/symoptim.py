@@ -308,6 +308,86 @@ class ModelFunction:
             "registered with (obj/constr/constr_jac_val/lag_hess_val); there "
             "is no stand-alone CPU evaluation in this package")
 
+    # -- structural half of the per-function operator interface --------------
+    # (the in-tree statement of what the glue asks of a model function is
+    # /root/reference/adfem.py:20-120: jac_nnz / jac_ind / jac_val,
+    # hess_nnz / hess_ind / hess_val, grad).  Indices are variable-local, the
+    # sample index is slowest (adfem.py:303-328); unlike adfem's dense blocks
+    # only structural nonzeros are listed, same-variable Hessian blocks keep
+    # the lower triangle including the diagonal.
+    def _ext(self, shape, core):
+        shape = tuple(np.atleast_1d(shape)) if not isinstance(shape, tuple) \
+            else shape
+        ncore = len(core)
+        ext = shape[:len(shape) - ncore]
+        if tuple(shape[len(ext):]) != tuple(core):
+            raise ValueError(f'{self.__name__}: shape {shape} does not end '
+                             f'with the core shape {tuple(core)}')
+        return int(np.prod(ext, dtype=np.int64)), len(ext) > 0
+
+    def _local(self, arg, dec_shapes, flats, M):
+        """[M, nnz] variable-local flat indices of core entries ``flats``."""
+        spec = self.spec
+        core = int(np.prod(spec.core[arg], dtype=np.int64))
+        rows, per_sample = self._ext(tuple(dec_shapes[arg]), spec.core[arg])
+        flats = np.asarray(flats, dtype=np.int64)
+        if not per_sample:
+            return np.broadcast_to(flats, (M, len(flats)))
+        if rows != M:
+            raise ValueError(f'{self.__name__}: {arg} has {rows} rows, the '
+                             f'output has {M}')
+        return np.arange(M, dtype=np.int64)[:, None] * core + flats
+
+    def jac_nnz(self, dec_shapes, out_shape):
+        M, _ = self._ext(tuple(np.atleast_1d(out_shape)), self.spec.out_core)
+        return M * sum(len(e) for e in self.spec.jac.values())
+
+    def jac_ind(self, dec_shapes, out_shape):
+        """``{(wrt,): int array (2, nnz)}`` rows ``[wrt index, out index]``."""
+        import collections
+        spec = self.spec
+        M, _ = self._ext(tuple(np.atleast_1d(out_shape)), spec.out_core)
+        out = collections.OrderedDict()
+        k = np.arange(M, dtype=np.int64)[:, None]
+        for wrt, entries in spec.jac.items():
+            w = self._local(wrt, dec_shapes, [e.index[0] for e in entries], M)
+            o = k * spec.out_size + np.array([e.index[1] for e in entries])
+            out[(wrt,)] = np.array([w.ravel(), o.ravel()])
+        return out
+
+    def hess_nnz(self, dec_shapes, out_shape):
+        M, _ = self._ext(tuple(np.atleast_1d(out_shape)), self.spec.out_core)
+        return M * sum(len(e) for e in self.spec.hess.values())
+
+    def hess_ind(self, dec_shapes, out_shape):
+        """``{(w0, w1): int array (3, nnz)}`` rows ``[w0, w1, out index]``."""
+        import collections
+        spec = self.spec
+        M, _ = self._ext(tuple(np.atleast_1d(out_shape)), spec.out_core)
+        out = collections.OrderedDict()
+        k = np.arange(M, dtype=np.int64)[:, None]
+        for (w0, w1), entries in spec.hess.items():
+            i0 = self._local(w0, dec_shapes, [e.index[0] for e in entries], M)
+            i1 = self._local(w1, dec_shapes, [e.index[1] for e in entries], M)
+            o = k * spec.out_size + np.array([e.index[2] for e in entries])
+            out[(w0, w1)] = np.array([i0.ravel(), i1.ravel(), o.ravel()])
+        return out
+
+    def _gpu_only(self, what):
+        raise RuntimeError(
+            f"{self.__name__}.{what}: derivative VALUES are produced by the "
+            "fused CUDA kernels of the Problem this function is registered "
+            "with (constr_jac_val / lag_hess_val / obj_grad)")
+
+    def jac_val(self, *args, **kwargs):
+        self._gpu_only('jac_val')
+
+    def hess_val(self, *args, **kwargs):
+        self._gpu_only('hess_val')
+
+    def grad(self, *args, **kwargs):
+        self._gpu_only('grad')
+
 
 class CompiledModel:
     """Base of the classes returned by ``Model.compile_class()``."""

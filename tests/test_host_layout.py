@@ -51,3 +51,39 @@ def test_views_are_writable(golden):
     cvec = np.zeros(p.ncons)
     p.unpack_constraints(cvec)['innovation'][:] = 2.0
     assert cvec.sum() == 2.0 * p.constraints['innovation'].block.size
+
+
+def test_function_level_indices_compose_to_the_problem_level(golden):
+    """The per-function operator interface (adfem.py:20-120: jac_ind /
+    hess_ind with variable-local indices) plus the problem's offsets gives
+    exactly the global COO index arrays."""
+    p = _problem(golden)
+    specs = {**p.decision, **p.dependent}
+    shapes = {n: s.shape for n, s in specs.items()}
+    rows, cols = [], []
+    for name, reg in p.constraints.items():
+        fun = getattr(p.model, name)
+        ind = fun.jac_ind(shapes, reg.block.shape)
+        assert fun.jac_nnz(shapes, reg.block.shape) == \
+            sum(v.shape[1] for v in ind.values())
+        for (wrt,), (w, o) in ind.items():
+            rows.append(reg.block.offset + o)
+            cols.append(specs[wrt].offset + w)
+    jr, jc = p.constr_jac_ind()
+    np.testing.assert_array_equal(np.concatenate(rows), jr)
+    np.testing.assert_array_equal(np.concatenate(cols), jc)
+    hrow, hcol = [], []
+    regs = list(p.objectives.items()) + list(p.constraints.items())
+    for name, reg in regs:
+        fun = getattr(p.model, name)
+        for (w0, w1), (i0, i1, o) in fun.hess_ind(shapes,
+                                                  reg.block.shape).items():
+            a, b = specs[w0].offset + i0, specs[w1].offset + i1
+            hrow.append(np.maximum(a, b))
+            hcol.append(np.minimum(a, b))
+    hr, hc = p.lag_hess_ind()
+    np.testing.assert_array_equal(np.concatenate(hrow), hr)
+    np.testing.assert_array_equal(np.concatenate(hcol), hc)
+    import pytest
+    with pytest.raises(RuntimeError):
+        p.model.dynamics.jac_val()
