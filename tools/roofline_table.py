@@ -1,0 +1,75 @@
+#!/usr/bin/env python3
+"""Device-resident throughput of one full callback set for every BASELINE
+configuration shape, as a JSON-lines table:
+kernel time (CUDA events, L2 flushed), algorithmic GB/s, fraction of the
+measured HBM peak, whole-step callback sets/s and samples/s."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import bench  # noqa: E402
+from colloc_fem_code_b200 import backend, families, synthetic  # noqa: E402
+
+CONFIGS = [
+    ('C1 hfb320-equivalent', 'ndisc_zoh', (4, 2, 7), 601),
+    ('C1 hfb320-equivalent', 'ndisc_zoh', (4, 2, 7), 1_000_000),
+    ('C2 attas_sp_ml', 'ml', (2, 1, 2), 1000),
+    ('C2 attas_sp_ml', 'ml', (2, 1, 2), 1_000_000),
+    ('C2 attas_sp_innov_bal', 'balanced', (2, 1, 2), 1_000_000),
+    ('C3 blackbox_innov_bal', 'balanced', (5, 3, 3), 250),
+    ('C3 blackbox_innov_bal', 'balanced', (5, 3, 3), 1_000_000),
+    ('C5 long trajectory', 'ml', (2, 1, 2), 10_000_000),
+    ('extension trapezoid', 'trapezoid', (2, 1, 2), 1_000_000),
+]
+
+
+def main():
+    peak, _ = bench.measured_peak()
+    for label, kind, dims, N in CONFIGS:
+        nx, nu, ny = dims
+        exp = synthetic.experiment(0, N, nx, nu, ny)
+        p = families.make_problem(kind, exp['y'], exp['u'], nx, dt=0.05)
+        dvec, lam, sigma = synthetic.evaluation_point(p, exp)
+        del exp
+        h = p.backend.handle
+        h.set_kernel_timing(True)
+        h.set_dvec(dvec)
+        h.set_multipliers(sigma, lam)
+        dptr = h.device_ptrs()['dvec']
+        steps = 20
+        for i in range(5):
+            h.flush_l2(256 << 20)
+            h.set_dvec_device(dptr)
+            h.eval(31)
+        h.synchronize()
+        step_ms = []
+        for i in range(steps):
+            h.flush_l2(256 << 20)
+            h.event_record(0)
+            h.set_dvec_device(dptr)
+            h.eval(31)
+            h.event_record(1)
+            step_ms.append(h.event_elapsed_ms(0, 1))
+        kms = float(np.median(h.sample_kernel_ms_history(steps)))
+        balg = bench.algorithmic_bytes_per_sample(nx, nu, ny)
+        if kind == 'trapezoid':
+            balg += 8 * nu          # u is read at k and k+1 but staged once
+        gbs = balg * N / (kms * 1e-3) / 1e9
+        sms = float(np.median(step_ms))
+        print(json.dumps({
+            'config': label, 'family': kind, 'dims': dims, 'N': N,
+            'kernel_ms': kms, 'step_ms': sms, 'algorithmic_GBps': gbs,
+            'frac_of_measured_peak': gbs / peak,
+            'callback_sets_per_s': 1e3 / sms,
+            'samples_per_s': N * 1e3 / sms,
+            'algorithmic_bytes_per_sample': balg}), flush=True)
+        p.backend.close()
+
+
+if __name__ == '__main__':
+    main()
