@@ -28,6 +28,26 @@ CONFIGS = [
 ]
 
 
+def structure_bytes_per_sample(st):
+    """Compulsory traffic per sample from the structure tables: every
+    per-sample input once (variables, data, multipliers), every per-sample
+    output once (constraint values, gradient block, Jacobian and Hessian
+    values)."""
+    n = sum(v['core'] for v in st.vars if v['per_sample'])
+    n += sum(d['core'] for d in st.data)
+    for f in st.funs:
+        if not f['per_sample']:
+            continue
+        if f['is_objective']:
+            n += sum(st.vars[r[1]]['core'] for a, r in f['args'].items()
+                     if r[0] == 'var' and a in f['spec'].jac)   # gradient block
+        else:
+            n += 2 * f['out_core']          # multipliers in, values out
+    n += sum(b['c'] for b in st.jac_blocks if st.funs[b['fun']]['per_sample'])
+    n += sum(b['c'] for b in st.hess_blocks if st.funs[b['fun']]['per_sample'])
+    return 8 * n
+
+
 def main():
     peak, _ = bench.measured_peak()
     for label, kind, dims, N in CONFIGS:
@@ -56,9 +76,9 @@ def main():
             h.event_record(1)
             step_ms.append(h.event_elapsed_ms(0, 1))
         kms = float(np.median(h.sample_kernel_ms_history(steps)))
-        balg = bench.algorithmic_bytes_per_sample(nx, nu, ny)
-        if kind == 'trapezoid':
-            balg += 8 * nu          # u is read at k and k+1 but staged once
+        balg = structure_bytes_per_sample(p.structure)
+        if kind != 'trapezoid':     # the closed form of SURVEY.md section 8(d)
+            assert balg == bench.algorithmic_bytes_per_sample(nx, nu, ny)
         gbs = balg * N / (kms * 1e-3) / 1e9
         sms = float(np.median(step_ms))
         print(json.dumps({
