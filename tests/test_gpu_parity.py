@@ -273,3 +273,25 @@ def test_batched_problems_match_single_problem_evaluation():
         for k, v in zip(('f', 'grad', 'g', 'jac', 'hess'), one):
             np.testing.assert_array_equal(np.ravel(out[k][b]), np.ravel(v),
                                           err_msg=f'{k} problem {b}')
+
+
+def test_reductions_are_bitwise_reproducible():
+    """No floating-point atomics, fixed summation tree: repeated launches
+    (different CTA scheduling, cold and warm caches) give identical bits for
+    the objective and the whole gradient."""
+    nx, nu, ny, N = 2, 1, 2, 300_000
+    exp = synthetic.experiment(4, N, nx, nu, ny)
+    p = families.make_problem('ml', exp['y'], exp['u'], nx)
+    dvec, lam, sigma = synthetic.evaluation_point(p, exp)
+    h = p.backend.handle
+    seen = set()
+    for rep in range(6):
+        if rep % 2:
+            h.flush_l2(256 << 20)
+        h.set_dvec(dvec)
+        h.set_multipliers(sigma, lam)
+        h.eval(backend.ALL if rep < 3 else backend.F | backend.GRAD)
+        f = h.fetch(backend.F).tobytes()
+        grad = h.fetch(backend.GRAD).tobytes()
+        seen.add((f, grad))
+    assert len(seen) == 1

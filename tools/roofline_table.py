@@ -81,8 +81,32 @@ def main():
             assert balg == bench.algorithmic_bytes_per_sample(nx, nu, ny)
         gbs = balg * N / (kms * 1e-3) / 1e9
         sms = float(np.median(step_ms))
+        extra = {}
+        if N <= 10_000:     # native script lengths: host-API latency + CPU
+            import time
+            from oracle import ref_models
+            host = backend.HostBuffers(h)
+            host.dvec[:] = dvec
+            host.lam[:] = lam
+            ts = []
+            for i in range(30):
+                t0 = time.perf_counter()
+                h.set_dvec(host.dvec)
+                h.set_multipliers(sigma, host.lam)
+                h.eval(31)
+                host.fetch_all()
+                ts.append(time.perf_counter() - t0)
+            extra['e2e_host_api_ms'] = 1e3 * float(np.median(ts[5:]))
+            o = ref_models.make_problem(kind, p.y, p.u, nx, dt=0.05)
+            tc = []
+            for i in range(4):
+                t0 = time.perf_counter()
+                o.obj(dvec), o.obj_grad(dvec), o.constr(dvec)
+                o.constr_jac_val(dvec), o.lag_hess_val(dvec, sigma, lam)
+                tc.append(time.perf_counter() - t0)
+            extra['cpu_oracle_ms'] = 1e3 * min(tc[1:])
         print(json.dumps({
-            'config': label, 'family': kind, 'dims': dims, 'N': N,
+            **extra, 'config': label, 'family': kind, 'dims': dims, 'N': N,
             'kernel_ms': kms, 'step_ms': sms, 'algorithmic_GBps': gbs,
             'frac_of_measured_peak': gbs / peak,
             'callback_sets_per_s': 1e3 / sms,
