@@ -51,6 +51,8 @@ def main():
     ap.add_argument('--samples', type=int, default=250)
     ap.add_argument('--tol', type=float, default=1e-6)
     ap.add_argument('--max-iter', type=int, default=200)
+    ap.add_argument('--workers', type=int, default=0,
+                    help='host worker processes (0: threads in one process)')
     args = ap.parse_args()
     import torch
     from colloc_fem_code_b200 import fit
@@ -63,7 +65,11 @@ def main():
              for i in range(args.problems)]
     problems = [c[0] for c in cases]
     db, cb, scaling = fit.ml_setup(problems[0])
-    bf = fit.BatchFitter(problems, device=local)
+    if args.workers:
+        bf = fit.ParallelBatchFitter(problems, device=local,
+                                     workers=args.workers)
+    else:
+        bf = fit.BatchFitter(problems, device=local)
     t0 = time.perf_counter()
     out = bf.fit([c[1] for c in cases], db, cb, scaling, tol=args.tol,
                  max_iter=args.max_iter)
@@ -79,14 +85,17 @@ def main():
         'batched_launch_rounds': bf.launches,
         'callback_requests': sum(i['callback_calls'] for _, i in out),
         'iterations_mean': float(np.mean([i['iterations'] for _, i in out])),
-        'host_threads': bf.threads, 'host_cores': os.cpu_count(),
+        'host_threads': getattr(bf, 'threads', None),
+        'host_worker_processes': getattr(bf, 'workers', None),
+        'host_cores': os.cpu_count(),
         'config': {'workload': 'mc_blackbox_cfem: ML+Balanced (5,3,3), '
                                f'N={args.samples}, {args.problems} problems '
                                'per GPU, lock-step batched callbacks',
                    'solver': 'builtin-ipm (no IPOPT in the image)',
                    'tol': args.tol, 'max_iter': args.max_iter},
     }
-    bf.close()
+    if hasattr(bf, 'close'):
+        bf.close()
     print(json.dumps(rec))
 
 

@@ -354,3 +354,174 @@ def balanced_guess(A, B, C):
     obs_orth = np.hstack((Ab.T * sW, Cb.T)) / sW[:, None]
     return T, {'A': Ab, 'B': Bb, 'C': Cb, 'sW_diag': sW,
                'ctrl_orth': ctrl_orth, 'obs_orth': obs_orth}
+
+
+class ParallelBatchFitter:
+    """``BatchFitter`` with the host work spread over worker PROCESSES.
+
+    The interior-point iterations (KKT factorisations, line-search logic) are
+    host work that Python threads cannot overlap; here ``workers`` processes
+    each advance a slice of the batch, while the parent -- the only process
+    that talks to the GPU -- serves every round's evaluation requests with one
+    batched launch.  Requests and results travel through anonymous shared
+    memory that the parent page-locks (``cfem_host_register``), so the DMA
+    engines read the workers' decision vectors and write the results in place.
+
+    Round protocol (two barriers):
+      workers  write x (and lambda) of their active problems + request kind
+      ---- barrier ----
+      parent   H2D, one fused launch for the whole batch, D2H
+      ---- barrier ----
+      workers  read their results, advance their solvers (in parallel)
+    """
+
+    def __init__(self, problems, device=0, workers=None):
+        import mmap
+        import multiprocessing as mp
+        from . import backend
+        self.problems = problems
+        p0 = problems[0]
+        st = p0.structure
+        key = st.key()
+        for p in problems[1:]:
+            if p.structure.key() != key or p.structure.N != st.N:
+                raise ValueError('a batch needs same-shaped problems')
+        for p in problems:          # index arrays: build once, before forking
+            p.constr_jac_ind()
+            p.lag_hess_ind()
+        self.B = B = len(problems)
+        self.workers = W = max(1, min(workers or (os.cpu_count() or 2) - 1, B))
+        self.sizes = sizes = {'dvec': p0.ndec, 'lam': p0.ncons, 'f': 1,
+                              'grad': p0.ndec, 'g': p0.ncons,
+                              'jac': p0.nnzjac, 'hess': p0.nnzhess}
+        self._maps, self.sh = {}, {}
+        for name, n in sizes.items():
+            nbytes = max(8, B * n * 8)
+            m = mmap.mmap(-1, nbytes)       # MAP_SHARED | MAP_ANONYMOUS
+            self._maps[name] = m
+            self.sh[name] = np.frombuffer(m, dtype=np.float64,
+                                          count=B * n).reshape(B, n)
+        mk = mmap.mmap(-1, max(8, B * 8))
+        self._maps['kind'] = mk
+        self.kind = np.frombuffer(mk, dtype=np.int64, count=B)
+        self.ctx = mp.get_context('fork')
+        self.barrier = self.ctx.Barrier(W + 1)
+        self.results = self.ctx.Queue()
+        self.device = device
+        self._st = st
+        self._backend = backend
+        self.launches = 0
+        self.seconds_gpu = 0.0
+
+    def _worker(self, mine, dec0s, dec_bounds, constr_bounds, scaling, tol,
+                max_iter):
+        from . import nlp
+        sh, kind = self.sh, self.kind
+        steps, requests, active = {}, {}, set(mine)
+
+        def per(i, arg):
+            return arg[i] if isinstance(arg, list) else arg
+        for i in mine:
+            s = nlp.InteriorPointSolver(_StructureOnly(self.problems[i]),
+                                        per(i, dec_bounds),
+                                        per(i, constr_bounds))
+            s.add_num_option('tol', tol)
+            s.add_int_option('max_iter', max_iter)
+            s.set_scaling(*per(i, scaling))
+            steps[i] = s.solve_steps(dec0s[i])
+            requests[i] = next(steps[i])
+        done = []
+        while True:
+            for i in mine:
+                if i in active:
+                    req = requests[i]
+                    sh['dvec'][i] = req[1]
+                    if req[0] == 'all':
+                        sh['lam'][i] = req[3]
+                        kind[i] = 2
+                    else:
+                        kind[i] = 1
+                else:
+                    kind[i] = 0
+            self.barrier.wait()         # requests are posted
+            self.barrier.wait()         # results are in shared memory
+            if kind[0] < 0:             # parent: everybody is done
+                break
+            for i in list(active):
+                if requests[i][0] == 'all':
+                    res = (float(sh['f'][i, 0]), sh['grad'][i].copy(),
+                           sh['g'][i].copy(), sh['jac'][i].copy(),
+                           sh['hess'][i].copy())
+                else:
+                    res = (float(sh['f'][i, 0]), sh['g'][i].copy())
+                try:
+                    requests[i] = steps[i].send(res)
+                except StopIteration as stop:
+                    x, info = stop.value
+                    done.append((i, x, {k: v for k, v in info.items()
+                                        if not isinstance(v, np.ndarray)}))
+                    active.discard(i)
+        self.results.put(done)
+
+    def fit(self, dec0s, dec_bounds, constr_bounds, scaling, tol=1e-8,
+            max_iter=300):
+        import time
+        backend = self._backend
+        B, W = self.B, self.workers
+        slices = [list(range(w, B, W)) for w in range(W)]
+        procs = [self.ctx.Process(target=self._worker,
+                                  args=(sl, dec0s, dec_bounds, constr_bounds,
+                                        scaling, tol, max_iter), daemon=True)
+                 for sl in slices]
+        for pr in procs:            # fork BEFORE this process touches CUDA
+            pr.start()
+        st = self._st
+        lib = backend.Library.for_structure(st)
+        data = [np.stack([np.ascontiguousarray(
+            p.structure.data[i]['source'], dtype=float)
+            for p in self.problems]) for i in range(len(st.data))]
+        h = backend.Handle(lib, st.N, data, st.scalar_values, batch=B,
+                           device=self.device)
+        registered = []
+        for name, arr in self.sh.items():
+            if lib.cfem_host_register(arr.ctypes.data, arr.nbytes) == 0:
+                registered.append(arr)
+        sigma = scaling[0][0] if isinstance(scaling, list) else scaling[0]
+        flat = {k: v.reshape(-1) for k, v in self.sh.items()}
+        flat['lam'][:] = 0.0
+        try:
+            while True:
+                self.barrier.wait()
+                kinds = self.kind.copy()
+                if not kinds.any():
+                    self.kind[0] = -1
+                    self.barrier.wait()
+                    break
+                t0 = time.perf_counter()
+                h.set_dvec(flat['dvec'])
+                if (kinds == 2).any():
+                    h.set_multipliers(sigma, flat['lam'])
+                    h.eval(backend.ALL)
+                    for bit, name in ((backend.F, 'f'), (backend.GRAD, 'grad'),
+                                      (backend.G, 'g'), (backend.JAC, 'jac'),
+                                      (backend.HESS, 'hess')):
+                        h.fetch_async(bit, flat[name])
+                else:
+                    h.eval(backend.F | backend.G)
+                    h.fetch_async(backend.F, flat['f'])
+                    h.fetch_async(backend.G, flat['g'])
+                h.synchronize()
+                self.seconds_gpu += time.perf_counter() - t0
+                self.launches += 1
+                self.barrier.wait()
+        finally:
+            for arr in registered:
+                lib.cfem_host_unregister(arr.ctypes.data)
+            h.close()
+        out = [None] * B
+        for _ in procs:
+            for i, x, info in self.results.get(timeout=600):
+                out[i] = (x, info)
+        for pr in procs:
+            pr.join(60)
+        return out

@@ -98,3 +98,21 @@ def test_ipopt_callback_grouping_against_fake_ipopt(tmp_path):
     np.testing.assert_allclose(L[2], o.obj_grad(dec0).sum(), rtol=1e-11)
     assert ev.kernel_groups == 3
     s.close()
+
+
+def test_parallel_batch_fitter_matches_thread_version():
+    cases = [_case(seed, 250) for seed in (3, 5, 11, 13, 17)]
+    problems = [c[1] for c in cases]
+    db, cb, scaling = cases[0][4]
+    dbs = [c[4][0] for c in cases]
+    pf = fit.ParallelBatchFitter(problems, workers=3)
+    par = pf.fit([c[3] for c in cases], dbs, cb, scaling, tol=1e-8,
+                 max_iter=400)
+    bf = fit.BatchFitter(problems)
+    ser = bf.fit([c[3] for c in cases], dbs, cb, scaling, tol=1e-8,
+                 max_iter=400)
+    bf.close()
+    for (xp, ip), (xs, is_) in zip(par, ser):
+        assert ip['status'] == is_['status'] == 'solved'
+        assert ip['iterations'] == is_['iterations']
+        np.testing.assert_array_equal(xp, xs)
