@@ -416,6 +416,11 @@ class ParallelBatchFitter:
     def _worker(self, mine, dec0s, dec_bounds, constr_bounds, scaling, tol,
                 max_iter):
         from . import nlp
+        try:                        # one BLAS thread per worker process
+            import threadpoolctl
+            threadpoolctl.threadpool_limits(1)
+        except Exception:
+            pass
         sh, kind = self.sh, self.kind
         steps, requests, active = {}, {}, set(mine)
 
