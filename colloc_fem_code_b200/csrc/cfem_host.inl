@@ -81,10 +81,7 @@ struct Layout {
 // registration order (cf. /root/reference/fem.py:36-57 for the order).
 static void compute_layout(long long N, int halo, Layout& L)
 {
-    // tuning experiment only: start every block on a 128-byte boundary (the
-    // product layout is dense, i.e. IPOPT-facing)
-    const bool align = getenv("CFEM_EXPERIMENT_ALIGN") != nullptr;
-    auto up = [align](long long v) { return align ? (v + 15) / 16 * 16 : v; };
+
     long long off = 0;
     for (int v = 0; v < gen::kNumVars; ++v) {
         const gen::VarDesc& d = gen::kVars[v];
@@ -106,7 +103,6 @@ static void compute_layout(long long N, int halo, Layout& L)
         }
         L.fun_rows[f] = rows;
         if (d.cons_index >= 0) {
-            coff = up(coff);
             L.cons_off[d.cons_index] = coff;
             coff += rows * d.out_core;
         }
@@ -114,14 +110,12 @@ static void compute_layout(long long N, int halo, Layout& L)
     L.ncons = coff;
     long long joff = 0;
     for (int b = 0; b < gen::kNumJacBlocks; ++b) {
-        joff = up(joff);
         L.jac_off[b] = joff;
         joff += L.fun_rows[gen::kJacBlocks[b].fun] * gen::kJacBlocks[b].c;
     }
     L.nnz_jac = joff;
     long long hoff = 0;
     for (int b = 0; b < gen::kNumHessBlocks; ++b) {
-        hoff = up(hoff);
         L.hess_off[b] = hoff;
         hoff += L.fun_rows[gen::kHessBlocks[b].fun] * gen::kHessBlocks[b].c;
     }

@@ -4,7 +4,7 @@ racecheck): every kernel variant, ragged tile sizes, halo shards, a batch."""
 import os
 import sys
 
-import numpy as np
+
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
