@@ -402,6 +402,27 @@ class Generator:
             out.append('        }')
             return out
 
+        def prefetch(tile_expr):
+            out = ['        {',
+                   f'            const long long r0 = ({tile_expr}) * {T};']
+            for key in sorted(lay['stor']):
+                st_ = lay['stor'][key]
+                if key[0] == 'var':
+                    src = f'dvec + a.var_off[{key[1]}]'
+                    rows = f'a.var_rows[{key[1]}]'
+                elif key[0] == 'data':
+                    src = (f'a.data[{key[1]}] + b * a.data_rows[{key[1]}] * '
+                           f'{st_["core"]}')
+                    rows = f'a.data_rows[{key[1]}]'
+                else:
+                    ci = self.funs[key[1]]['cons_index']
+                    src = f'a.lam + b * a.ncons + a.cons_off[{ci}]'
+                    rows = f'a.fun_rows[{key[1]}]'
+                out.append(f'            cfem::prefetch_rows_l2<{st_["core"]}, '
+                           f'{st_["nrows"]}>({src}, {rows}, r0, tid);')
+            out.append('        }')
+            return out
+
         # persistent CTAs: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the
         # inputs of the next tile are in flight (cp.async) while this one is
         # evaluated and streamed out
@@ -411,6 +432,8 @@ class Generator:
         w.append('    if (tile < a.ntiles)')
         w += stage('tile', '0')
         w.append('    cfem::cp_async_commit();')
+        w.append('    if (a.prefetch_tiles > 0 && tile + a.prefetch_tiles < a.ntiles)')
+        w += prefetch('tile + a.prefetch_tiles')
         w.append('    for (; tile < a.ntiles; tile += tstride, buf ^= 1) {')
         w.append('    if (tile + tstride < a.ntiles)')
         w += stage('tile + tstride', 'buf ^ 1')
@@ -807,7 +830,7 @@ class Generator:
         w.append('// Persistent launch: at most `max_ctas` CTAs per problem '
                  '(resident CTAs per SM x SMs x waves), each looping over tiles.')
         w.append('static cudaError_t launch_sample(unsigned mask, int batch, '
-                 'int sm_count, int waves, cudaStream_t s, cfem::KArgs a)')
+                 'int sm_count, int waves, long long prefetch, cudaStream_t s, cfem::KArgs a)')
         w.append('{')
         w.append('    int per_sm = 1;')
         w.append('    for (int i = 0; i < kNumMasks; ++i) '
@@ -816,6 +839,10 @@ class Generator:
         w.append('    if (gx < 1) gx = 1;')
         w.append('    if (gx > a.ntiles) gx = a.ntiles;')
         w.append('    a.nctas = gx;')
+        w.append('    // CTAs that start one "resident set" later find their inputs in L2')
+        w.append('    a.prefetch_tiles = prefetch < 0 ? (long long)per_sm * sm_count '
+                 '/ batch : prefetch;')
+        w.append('    if (gx < a.ntiles) a.prefetch_tiles = 0;   // persistent: cp.async double buffering instead')
         w.append('    a.ngroups = (gx + cfem::kReduceGroup - 1) / '
                  'cfem::kReduceGroup;')
         w.append('    const dim3 grid((unsigned)gx, (unsigned)batch);')

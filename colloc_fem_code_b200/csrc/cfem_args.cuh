@@ -31,6 +31,7 @@ struct KArgs {
     double* partials;       // [batch][ntiles][nreduce]
     // two-level deterministic reduction tree (all counters zero between launches)
     long long     nctas;        // CTAs per problem of this launch (<= ntiles)
+    long long     prefetch_tiles;   // L2 prefetch distance in tiles (0: off)
     long long     ngroups;      // ceil(nctas / kReduceGroup)
     double*       gpartials;    // [batch][ngroups][nreduce]
     unsigned int* group_count;  // [batch][ngroups] CTAs retired per group

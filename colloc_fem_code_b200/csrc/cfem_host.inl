@@ -20,6 +20,7 @@ struct cfem_problem {
     int           device = 0;
     int           sm_count = 1;
     int           waves = 8;            // CTAs launched <= resident CTAs x waves (B200 sweep)
+    long long     prefetch = 0;         // L2 prefetch distance in tiles; < 0: one resident set
     cudaStream_t  stream = nullptr;
     bool          own_stream = false;
     cudaStream_t  aux_stream = nullptr;     // parameter-only kernel, concurrent
@@ -222,6 +223,7 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     p->device = device;
     p->sm_count = sm_count;
     if (const char* w = getenv("CFEM_WAVES")) { p->waves = atoi(w) > 0 ? atoi(w) : 1; }
+    if (const char* w = getenv("CFEM_PREFETCH")) { p->prefetch = atoll(w); }
     p->N = n_samples;
     p->batch = batch;
     p->halo = halo;
@@ -409,7 +411,7 @@ int cfem_eval(cfem_problem* p, uint32_t what)
     }
     const int slot = (int)(p->kev_count % cfem_problem::kTimingRing);
     if (p->timing) CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot], p->stream));
-    CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->stream, p->k));
+    CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, p->stream, p->k));
     if (p->timing) {
         CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot + 1], p->stream));
         p->kev_count += 1;
