@@ -386,6 +386,8 @@ class ParallelBatchFitter:
         for p in problems[1:]:
             if p.structure.key() != key or p.structure.N != st.N:
                 raise ValueError('a batch needs same-shaped problems')
+        from . import nlp
+        nlp.warm_up()               # JIT-compile before forking
         for p in problems:          # index arrays: build once, before forking
             p.constr_jac_ind()
             p.lag_hess_ind()

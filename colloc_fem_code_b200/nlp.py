@@ -239,6 +239,33 @@ class Solver:
 # built-in interior-point driver
 # ----------------------------------------------------------------------------
 
+def _bt_negative_py(D, E):
+    """Negative-eigenvalue count of a symmetric block-tridiagonal matrix
+    (diagonal blocks D[i], sub-diagonal blocks E[i]) by the Schur recursion
+    S_{i+1} = D_{i+1} - E_i S_i^-1 E_i'; -1 if a pivot block is numerically
+    singular."""
+    neg = 0
+    S = D[0].copy()
+    nblk = D.shape[0]
+    for i in range(nblk):
+        S = 0.5 * (S + S.T)
+        ev_ = np.linalg.eigvalsh(S)
+        big = max(1.0, np.max(np.abs(ev_)))
+        if np.min(np.abs(ev_)) <= 1e-13 * big:
+            return -1
+        neg += int((ev_ < 0).sum())
+        if i + 1 < nblk:
+            S = D[i + 1] - E[i] @ np.linalg.solve(S, E[i].T)
+    return neg
+
+
+try:        # the recursion is sequential over samples: compile it if we can
+    import numba as _numba
+    _bt_negative = _numba.njit(cache=True)(_bt_negative_py)
+except Exception:       # pragma: no cover - numba is optional
+    _bt_negative = _bt_negative_py
+
+
 class BorderedBandKKT:
     """Host solver for the KKT systems of the filter-error problems.
 
@@ -321,24 +348,15 @@ class BorderedBandKKT:
         ri, rj = pos_in[coo.row], pos_in[coo.col]
         D = np.zeros((nblk, w, w))
         E = np.zeros((max(nblk - 1, 1), w, w))
-        dmask = bi == bj
-        np.add.at(D, (bi[dmask], ri[dmask], rj[dmask]), coo.data[dmask])
+        dmask = bi == bj            # (a CSR-derived COO has no duplicates)
+        D[bi[dmask], ri[dmask], rj[dmask]] = coo.data[dmask]
         emask = bi == bj + 1
-        np.add.at(E, (bj[emask], ri[emask], rj[emask]), coo.data[emask])
+        E[bj[emask], ri[emask], rj[emask]] = coo.data[emask]
         for i in np.flatnonzero(sizes < w):     # identity padding
             idx = np.arange(sizes[i], w)
             D[i, idx, idx] = 1.0
-        neg = 0
-        S = D[0]
-        for i in range(nblk):
-            S = 0.5 * (S + S.T)
-            ev_ = np.linalg.eigvalsh(S)
-            if np.min(np.abs(ev_)) <= 1e-13 * max(1.0, np.max(np.abs(ev_))):
-                return None
-            neg += int((ev_ < 0).sum())
-            if i + 1 < nblk:
-                S = D[i + 1] - E[i] @ np.linalg.solve(S, E[i].T)
-        return neg
+        neg = _bt_negative(D, np.ascontiguousarray(E))
+        return None if neg < 0 else int(neg)
 
     def solve(self, H, J, delta_w, delta_c, rhs, want_inertia=False):
         n, m = H.shape[0], J.shape[0]
@@ -1003,6 +1021,12 @@ class IpoptSolver(Solver):
             self.lib.FreeIpoptProblem(self._nlp)
             self._nlp = None
         super().close()
+
+
+def warm_up():
+    """Compile the optional numba kernels now (e.g. before forking workers)."""
+    D = np.stack([np.eye(2), -np.eye(2)])
+    _bt_negative(D, np.zeros((1, 2, 2)))
 
 
 def make_solver(problem, dec_bounds, constr_bounds, evaluator=None):
