@@ -34,6 +34,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
 
 F, GRAD, G, JAC, HESS, ALL = 1, 2, 4, 8, 16, 31
+X, LAMBDA = 32, 64
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 _c_int64_p = ctypes.POINTER(ctypes.c_int64)
@@ -69,6 +70,15 @@ ABI = {
                                   ctypes.c_void_p]),
     'cfem_fetch_async': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32,
                                         ctypes.c_void_p]),
+    'cfem_upload_pieces': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32,
+                                          ctypes.c_void_p, ctypes.c_int32,
+                                          ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p]),
+    'cfem_fetch_pieces': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32,
+                                         ctypes.c_void_p, ctypes.c_int32,
+                                         ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p]),
+    'cfem_set_obj_factor': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double]),
     'cfem_eval_f': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'cfem_eval_grad_f': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'cfem_eval_g': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
@@ -360,6 +370,29 @@ class Handle:
         valid after :meth:`synchronize`."""
         self._check(self.lib.cfem_fetch_async(self._ptr, int(which),
                                               out.ctypes.data))
+
+    @staticmethod
+    def _piece_arrays(pieces):
+        arr = np.ascontiguousarray(pieces, dtype=np.int64).reshape(-1, 3)
+        return (len(arr), np.ascontiguousarray(arr[:, 0]),
+                np.ascontiguousarray(arr[:, 1]),
+                np.ascontiguousarray(arr[:, 2]))
+
+    def upload_pieces(self, which, host_vector, pieces):
+        """``pieces``: rows (device offset, host offset, length) in doubles."""
+        n, dev, host, ln = self._piece_arrays(pieces)
+        self._check(self.lib.cfem_upload_pieces(
+            self._ptr, int(which), host_vector.ctypes.data, n,
+            dev.ctypes.data, host.ctypes.data, ln.ctypes.data))
+
+    def fetch_pieces(self, which, host_vector, pieces):
+        n, dev, host, ln = self._piece_arrays(pieces)
+        self._check(self.lib.cfem_fetch_pieces(
+            self._ptr, int(which), host_vector.ctypes.data, n,
+            dev.ctypes.data, host.ctypes.data, ln.ctypes.data))
+
+    def set_obj_factor(self, sigma):
+        self._check(self.lib.cfem_set_obj_factor(self._ptr, float(sigma)))
 
     def synchronize(self):
         self._check(self.lib.cfem_synchronize(self._ptr))

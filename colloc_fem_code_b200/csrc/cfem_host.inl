@@ -454,6 +454,70 @@ int cfem_fetch(cfem_problem* p, uint32_t which, double* host_out)
     return CFEM_OK;
 }
 
+// Piecewise transfers between a (shared, page-locked) host vector in the
+// GLOBAL order of a time-sharded problem and this rank's device arrays.
+int cfem_upload_pieces(cfem_problem* p, uint32_t which, const double* host_base,
+                       int32_t n, const int64_t* dev_off, const int64_t* host_off,
+                       const int64_t* len)
+{
+    if (!p || !host_base || n < 0 || (n > 0 && (!dev_off || !host_off || !len))) return CFEM_EINVAL;
+    double* dst = nullptr;
+    long long cap = 0;
+    if (which == CFEM_X) { dst = p->d_dvec; cap = (long long)p->batch * p->k.ndec; }
+    else if (which == CFEM_LAMBDA) { dst = p->d_lam; cap = (long long)p->batch * p->k.ncons; }
+    else return CFEM_EINVAL;
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    for (int i = 0; i < n; ++i) {
+        if (len[i] <= 0) continue;
+        if (dev_off[i] < 0 || dev_off[i] + len[i] > cap)
+            return cfem::fail(p, CFEM_EINVAL, "cfem_upload_pieces: piece outside the device array", cudaSuccess);
+        CFEM_CUDA(p, cudaMemcpyAsync(dst + dev_off[i], host_base + host_off[i],
+                                     (size_t)len[i] * sizeof(double),
+                                     cudaMemcpyHostToDevice, p->stream));
+    }
+    if (which == CFEM_X) { p->k.dvec = p->d_dvec; p->have_dvec = true; p->valid = 0; }
+    else { p->k.lam = p->d_lam; p->have_lam = true; p->valid &= ~CFEM_HESS; }
+    return CFEM_OK;
+}
+
+int cfem_fetch_pieces(cfem_problem* p, uint32_t which, double* host_base,
+                      int32_t n, const int64_t* dev_off, const int64_t* host_off,
+                      const int64_t* len)
+{
+    if (!p || !host_base || n < 0 || (n > 0 && (!dev_off || !host_off || !len))) return CFEM_EINVAL;
+    const double* src = nullptr;
+    long long cap = 0;
+    const long long B = p->batch;
+    switch (which) {
+        case CFEM_F:    src = p->k.f;    cap = B; break;
+        case CFEM_GRAD: src = p->k.grad; cap = B * p->k.ndec; break;
+        case CFEM_G:    src = p->k.g;    cap = B * p->k.ncons; break;
+        case CFEM_JAC:  src = p->k.jac;  cap = B * p->k.nnz_jac; break;
+        case CFEM_HESS: src = p->k.hess; cap = B * p->k.nnz_hess; break;
+        default: return CFEM_EINVAL;
+    }
+    if (!(p->valid & which))
+        return cfem::fail(p, CFEM_ESTATE, "cfem_fetch_pieces: result not evaluated", cudaSuccess);
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    for (int i = 0; i < n; ++i) {
+        if (len[i] <= 0) continue;
+        if (dev_off[i] < 0 || dev_off[i] + len[i] > cap)
+            return cfem::fail(p, CFEM_EINVAL, "cfem_fetch_pieces: piece outside the device array", cudaSuccess);
+        CFEM_CUDA(p, cudaMemcpyAsync(host_base + host_off[i], src + dev_off[i],
+                                     (size_t)len[i] * sizeof(double),
+                                     cudaMemcpyDeviceToHost, p->stream));
+    }
+    return CFEM_OK;
+}
+
+int cfem_set_obj_factor(cfem_problem* p, double obj_factor)
+{
+    if (!p) return CFEM_EINVAL;
+    p->k.obj_factor = obj_factor;
+    p->valid &= ~CFEM_HESS;
+    return CFEM_OK;
+}
+
 static int cfem_eval_fetch(cfem_problem* p, uint32_t which, double* out)
 {
     if (!p) return CFEM_EINVAL;

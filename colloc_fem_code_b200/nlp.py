@@ -88,6 +88,20 @@ def time_structure_of(decision, constraints, sample_vars, sample_cons):
     return var_t, con_t
 
 
+def problem_time_structure(p):
+    """``time_structure_of`` for an ``optim.Problem``."""
+    st = p.structure
+    dec = {n_: (s_.offset, s_.shape) for n_, s_ in p.decision.items()}
+    con = {n_: (r.block.offset, r.block.shape)
+           for n_, r in p.constraints.items()}
+    svars = [v['name'] for v in st.vars if v['per_sample']]
+    scons = {f['name']: max([r[2] for r in f['args'].values()
+                             if r[0] == 'var'], default=0)
+             for f in st.funs
+             if f['per_sample'] and not f['is_objective']}
+    return time_structure_of(dec, con, svars, scons)
+
+
 class GpuEvaluator(Evaluator):
     """Callbacks served by the fused CUDA kernels of ``problem.backend``.
 
@@ -111,17 +125,7 @@ class GpuEvaluator(Evaluator):
         return self.problem.lag_hess_ind()
 
     def time_structure(self):
-        p = self.problem
-        st = p.structure
-        dec = {n_: (s_.offset, s_.shape) for n_, s_ in p.decision.items()}
-        con = {n_: (r.block.offset, r.block.shape)
-               for n_, r in p.constraints.items()}
-        svars = [v['name'] for v in st.vars if v['per_sample']]
-        scons = {f['name']: max([r[2] for r in f['args'].values()
-                                 if r[0] == 'var'], default=0)
-                 for f in st.funs
-                 if f['per_sample'] and not f['is_objective']}
-        return time_structure_of(dec, con, svars, scons)
+        return problem_time_structure(self.problem)
 
     def _set_x(self, x):
         self.buf.dvec[:] = x

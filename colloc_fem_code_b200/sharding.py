@@ -19,6 +19,8 @@ rank redundantly (they are O(1)); rank ``world-1`` (the one without halo) is
 their owner when results are gathered.
 """
 
+import os
+
 import numpy as np
 
 
@@ -92,29 +94,55 @@ class TimeShard:
         return out
 
     # -- inputs ------------------------------------------------------------------
-    def local_dvec(self, dvec):
-        out = np.empty(self.loc.ndec)
-        for i, v in enumerate(self.st.vars):
-            c = v['core']
-            lo, n = self.loc.var_off[i], self.loc.var_rows[i] * c
-            if v['per_sample']:
-                g0 = self.glob.var_off[i] + self.k0 * c
-            else:
-                g0 = self.glob.var_off[i]
-            out[lo:lo + n] = dvec[g0:g0 + n]
+    def input_pieces(self, kind):
+        """``(local offset, global offset, length)`` rows (in doubles) of the
+        rank-local decision vector (``'dvec'``) / multipliers (``'lam'``): the
+        argument of ``cfem_upload_pieces``.  Parameters (and the multipliers
+        of the parameter-only constraints) are replicated on every rank; the
+        halo row of a per-sample variable is read from the right neighbour's
+        range of the global vector."""
+        rows = []
+        if kind == 'dvec':
+            for i, v in enumerate(self.st.vars):
+                c = v['core']
+                g0 = self.glob.var_off[i] + (self.k0 * c if v['per_sample']
+                                             else 0)
+                rows.append((self.loc.var_off[i], g0,
+                             self.loc.var_rows[i] * c))
+        elif kind == 'lam':
+            for fi, f in enumerate(self.st.funs):
+                if f['cons_index'] < 0:
+                    continue
+                c = f['out_core']
+                g0 = self.glob.cons_off[fi] + (self.k0 * c if f['per_sample']
+                                               else 0)
+                rows.append((self.loc.cons_off[fi], g0,
+                             self.loc.fun_rows[fi] * c))
+        else:
+            raise KeyError(kind)
+        return np.asarray(rows, dtype=np.int64).reshape(-1, 3)
+
+    def result_pieces(self, kind):
+        """``(local offset, global offset, length)`` rows of the part of a
+        result this rank owns (``cfem_fetch_pieces``); ``'f'`` belongs to the
+        rank that owns the parameter-only functions."""
+        if kind == 'f':
+            rows = [(0, 0, 1)] if self.owns_params else []
+        else:
+            rows = [(l0, g0, n) for g0, l0, n in self._pairs(kind)]
+        return np.asarray(rows, dtype=np.int64).reshape(-1, 3)
+
+    def _gather(self, kind, vec, size):
+        out = np.empty(size)
+        for l0, g0, n in self.input_pieces(kind):
+            out[l0:l0 + n] = vec[g0:g0 + n]
         return out
 
+    def local_dvec(self, dvec):
+        return self._gather('dvec', dvec, self.loc.ndec)
+
     def local_multipliers(self, lam):
-        out = np.empty(self.loc.ncons)
-        for fi, f in enumerate(self.st.funs):
-            if f['cons_index'] < 0:
-                continue
-            c = f['out_core']
-            lo, n = self.loc.cons_off[fi], self.loc.fun_rows[fi] * c
-            g0 = self.glob.cons_off[fi] + (self.k0 * c if f['per_sample']
-                                           else 0)
-            out[lo:lo + n] = lam[g0:g0 + n]
-        return out
+        return self._gather('lam', lam, self.loc.ncons)
 
     # -- results: (global slice, local slice) pairs ------------------------------
     def _pairs(self, kind):
@@ -225,3 +253,306 @@ class ShardedEvaluator:
         self.handle.set_dvec(self.shard.local_dvec(dvec))
         self.handle.set_multipliers(obj_factor,
                                     self.shard.local_multipliers(lam))
+
+
+# -----------------------------------------------------------------------------
+# one solver process in front of all ranks
+# -----------------------------------------------------------------------------
+
+class SharedVectors:
+    """The solver-facing vectors of a time-sharded problem -- decision vector,
+    multipliers, objective, gradient, constraints, Jacobian and Hessian values,
+    all in the GLOBAL (IPOPT) order -- in ONE shared-memory segment that every
+    rank maps.  Each rank page-locks its mapping (``cfem_host_register``) so
+    that its GPU's DMA engines move the rank's pieces straight between this
+    memory and the device arrays over the rank's own PCIe link; the solver
+    process reads complete vectors without any gather step.
+
+    The segment starts with a control block of int64 words:
+    ``[0]`` request sequence number, ``[1]`` request (result mask | CFEM_X |
+    CFEM_LAMBDA, or ``STOP``), ``[2]`` obj_factor (float64 bits),
+    ``[8 + r]`` sequence number rank ``r`` has completed.
+    """
+
+    FIELDS = ('dvec', 'lam', 'f', 'grad', 'g', 'jac', 'hess')
+    STOP = -1
+    _CTRL = 8
+
+    def __init__(self, sizes, world, path=None):
+        import mmap
+        import uuid
+        self.world = world
+        self.sizes = {k: int(sizes[k]) for k in self.FIELDS}
+        nctrl = self._CTRL + world
+        nctrl += (-nctrl) % 8                   # 64-byte aligned vectors
+        total = 8 * (nctrl + sum(n + (-n) % 8 for n in self.sizes.values()))
+        self.created = path is None
+        if path is None:
+            path = f'/dev/shm/cfem_{os.getpid()}_{uuid.uuid4().hex[:12]}'
+            fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            os.ftruncate(fd, total)
+        else:
+            fd = os.open(path, os.O_RDWR)
+        self.path = path
+        try:
+            self._map = mmap.mmap(fd, total)
+        finally:
+            os.close(fd)
+        self.ctrl = np.frombuffer(self._map, dtype=np.int64, count=nctrl)
+        self._sigma = np.frombuffer(self._map, dtype=np.float64, count=nctrl)
+        off = 8 * nctrl
+        for k in self.FIELDS:
+            n = self.sizes[k]
+            setattr(self, k, np.frombuffer(self._map, dtype=np.float64,
+                                           count=n, offset=off))
+            off += 8 * (n + (-n) % 8)
+        self.nbytes = total
+        self._registered = None
+
+    def unlink(self):
+        """Remove the name (the mappings stay valid); creator only."""
+        if self.created and self.path:
+            try:
+                os.unlink(self.path)
+            except FileNotFoundError:
+                pass
+            self.path = None
+
+    def page_lock(self, lib):
+        base = self.ctrl.ctypes.data
+        if lib.cfem_host_register(base, self.nbytes) == 0:
+            self._registered = (lib, base)
+        return self._registered is not None
+
+    def close(self):
+        if self._registered:
+            lib, base = self._registered
+            lib.cfem_host_unregister(base)
+            self._registered = None
+        self.unlink()
+
+    @property
+    def sigma(self):
+        return float(self._sigma[2])
+
+    @sigma.setter
+    def sigma(self, value):
+        self._sigma[2] = value
+
+
+class SolverFacingEvaluator:
+    """All ranks of a time-sharded problem behind ONE NLP solver process.
+
+    Rank 0 runs the solver (``nlp.make_solver(problem, ..., evaluator=this)``
+    -- this object has the ``nlp.Evaluator`` surface); the other ranks call
+    ``serve()``.  A callback posts a request in the control block of the
+    ``SharedVectors``; every rank (rank 0 included) then uploads ITS pieces of
+    x / lambda, runs the fused kernels on its shard (objective and parameter
+    gradient are reduced across GPUs inside the kernel over NVLink peer memory,
+    or by ``allreduce`` when that is unavailable), writes ITS pieces of the
+    results into the shared vectors and acknowledges.  No rank ever touches
+    another rank's slice and nothing is gathered through the solver process.
+
+    ``handle`` needs ``upload_pieces``, ``fetch_pieces``, ``set_obj_factor``,
+    ``eval`` and ``synchronize`` (``backend.Handle``); ``reduce_hook(handle)``,
+    if given, is called after every evaluation that produced the objective or
+    the gradient (e.g. ``all_reduce`` + ``apply_reduced``).  ``broadcast`` is
+    ``torch.distributed.broadcast_object_list``-like and only used once, to
+    share the segment's name.
+    """
+
+    RESULTS = ((1, 'f'), (2, 'grad'), (4, 'g'), (8, 'jac'), (16, 'hess'))
+    X, LAMBDA = 32, 64
+
+    def __init__(self, problem, shard, handle, rank, world, broadcast,
+                 barrier, reduce_hook=None, lib=None):
+        self.problem, self.shard, self.h = problem, shard, handle
+        self.rank, self.world = rank, world
+        self.reduce_hook = reduce_hook
+        self.n, self.m = shard.glob.ndec, shard.glob.ncons
+        sizes = {'dvec': self.n, 'lam': self.m, 'f': 1, 'grad': self.n,
+                 'g': self.m, 'jac': shard.glob.nnz_jac,
+                 'hess': shard.glob.nnz_hess}
+        if rank == 0:
+            self.sv = SharedVectors(sizes, world)
+            self.sv.ctrl[:] = 0
+            self.sv.lam[:] = 0.0
+            broadcast([self.sv.path])
+        else:
+            box = [None]
+            broadcast(box)
+            self.sv = SharedVectors(sizes, world, path=box[0])
+        barrier()                       # everybody has mapped the segment
+        self.sv.unlink()
+        self.pinned = self.sv.page_lock(lib) if lib is not None else False
+        self._in = {k: shard.input_pieces(k) for k in ('dvec', 'lam')}
+        self._out = {k: shard.result_pieces(k)
+                     for _, k in self.RESULTS}
+        self._seq = 0
+        self._have_x = False
+        self._fresh = 0
+        self.seconds = 0.0
+        self.calls = 0
+        self.kernel_groups = 0
+
+    # -- what every rank does for one request ----------------------------------
+    def _execute(self, request):
+        h, sv = self.h, self.sv
+        if request & self.X:
+            h.upload_pieces(self.X, sv.dvec, self._in['dvec'])
+        if request & self.LAMBDA:
+            h.upload_pieces(self.LAMBDA, sv.lam, self._in['lam'])
+            h.set_obj_factor(sv.sigma)
+        mask = request & 31
+        h.eval(mask)
+        if self.reduce_hook is not None and mask & 3:
+            self.reduce_hook(h)
+        for bit, name in self.RESULTS:
+            if mask & bit and len(self._out[name]):
+                h.fetch_pieces(bit, getattr(sv, name), self._out[name])
+        h.synchronize()
+
+    @staticmethod
+    def _wait(cond):
+        import time
+        t0 = time.perf_counter()
+        while not cond():
+            if time.perf_counter() - t0 > 2e-3:
+                time.sleep(1e-4)        # long host phases: stop burning a core
+
+    def serve(self):
+        """Ranks other than 0: execute requests until the solver stops."""
+        sv, ctrl = self.sv, self.sv.ctrl
+        seq = 0
+        while True:
+            self._wait(lambda: ctrl[0] != seq)
+            seq = int(ctrl[0])
+            request = int(ctrl[1])
+            if request == SharedVectors.STOP:
+                ctrl[SharedVectors._CTRL + self.rank] = seq
+                return
+            self._execute(request)
+            ctrl[SharedVectors._CTRL + self.rank] = seq
+
+    def _request(self, request):
+        """Rank 0: post, do the own share, wait for everybody."""
+        sv, ctrl = self.sv, self.sv.ctrl
+        self._seq += 1
+        ctrl[1] = request
+        ctrl[0] = self._seq             # published last (x86 store order)
+        if request != SharedVectors.STOP:
+            self._execute(request)
+        ctrl[SharedVectors._CTRL] = self._seq
+        done = ctrl[SharedVectors._CTRL:SharedVectors._CTRL + self.world]
+        self._wait(lambda: (done == self._seq).all())
+
+    def stop(self):
+        if self.rank == 0 and self._seq >= 0:
+            self._request(SharedVectors.STOP)
+            self._seq = -1
+
+    def close(self):
+        self.stop()
+        self.sv.close()
+
+    # -- nlp.Evaluator surface (rank 0) ----------------------------------------
+    def jac_structure(self):
+        return self.problem.constr_jac_ind()
+
+    def hess_structure(self):
+        return self.problem.lag_hess_ind()
+
+    def time_structure(self):
+        from . import nlp
+        return nlp.problem_time_structure(self.problem)
+
+    def eval_fg(self, x):
+        import time
+        t0 = time.perf_counter()
+        self.sv.dvec[:] = x
+        self._request(self.X | 1 | 4)
+        self.seconds += time.perf_counter() - t0
+        self.calls += 1
+        return float(self.sv.f[0]), self.sv.g.copy()
+
+    def eval_all(self, x, sigma, lam):
+        import time
+        t0 = time.perf_counter()
+        sv = self.sv
+        sv.dvec[:] = x
+        sv.lam[:] = lam
+        sv.sigma = sigma
+        self._request(self.X | self.LAMBDA | 31)
+        self.seconds += time.perf_counter() - t0
+        self.calls += 1
+        return (float(sv.f[0]), sv.grad.copy(), sv.g.copy(), sv.jac.copy(),
+                sv.hess.copy())
+
+    _GROUP = {1: 1 | 4, 4: 1 | 4, 2: 1 | 2 | 4 | 8, 8: 1 | 2 | 4 | 8, 16: 16}
+
+    def ipopt_eval(self, which, x, new_x, out, sigma=None, lam=None):
+        """One IPOPT callback (same grouping as ``nlp.GpuEvaluator``)."""
+        import time
+        t0 = time.perf_counter()
+        sv = self.sv
+        flags = 0
+        if new_x or not self._have_x:
+            sv.dvec[:] = x
+            self._have_x, self._fresh, flags = True, 0, self.X
+        if which == 16:
+            sv.lam[:] = lam
+            sv.sigma = sigma
+            flags |= self.LAMBDA
+            self._fresh &= ~16
+        if not (self._fresh & which):
+            mask = self._GROUP[which]
+            self._request(flags | mask)
+            self._fresh |= mask
+            self.kernel_groups += 1
+        name = dict(self.RESULTS)[which]
+        out[...] = getattr(sv, name) if which != 1 else sv.f[0]
+        self.seconds += time.perf_counter() - t0
+        self.calls += 1
+
+
+def solver_facing_evaluator(problem, rank, world, device=0, group=None,
+                            reduce='peer'):
+    """``SolverFacingEvaluator`` on the CUDA backend under an initialised
+    ``torch.distributed`` process group (one process per GPU)."""
+    import torch
+    import torch.distributed as dist
+    ev = ShardedEvaluator(problem, rank, world, device=device)
+    hook = None
+    if world > 1:
+        mode = reduce
+        if mode == 'peer':
+            try:
+                ev.enable_peer_reduce(group)
+            except Exception:
+                mode = 'nccl'
+            ok = torch.tensor([mode == 'peer'], dtype=torch.int32,
+                              device=f'cuda:{device}')
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if mode == 'peer' and int(ok.item()) == 0:
+                ev.handle.set_peers(0, 1, [], [])
+                mode = 'nccl'
+        if mode != 'peer':
+            ptr = ev.handle.device_ptrs()['reduce']
+
+            class _Reduce:
+                __cuda_array_interface__ = {
+                    'shape': (ev.n_reduce,), 'typestr': '<f8',
+                    'data': (int(ptr), False), 'version': 2}
+            red = torch.as_tensor(_Reduce(), device=f'cuda:{device}')
+
+            def hook(h):
+                dist.all_reduce(red, group=group)
+                h.apply_reduced(ptr)
+    out = SolverFacingEvaluator(
+        problem, ev.shard, ev.handle, rank, world,
+        broadcast=lambda box: dist.broadcast_object_list(box, src=0,
+                                                         group=group),
+        barrier=lambda: dist.barrier(group), reduce_hook=hook,
+        lib=ev.lib)
+    out.sharded = ev
+    return out

@@ -67,6 +67,9 @@ extern "C" {
 #define CFEM_JAC   8u    /* constraint Jacobian COO values           */
 #define CFEM_HESS 16u    /* Lagrangian Hessian COO values            */
 #define CFEM_ALL  31u
+/* input selectors of cfem_upload_pieces() */
+#define CFEM_X      32u  /* decision vector                          */
+#define CFEM_LAMBDA 64u  /* constraint multipliers                   */
 
 typedef struct cfem_problem cfem_problem;   /* opaque */
 
@@ -128,6 +131,20 @@ int          cfem_fetch(cfem_problem* p, uint32_t which, double* host_out);
 /* Same copy without the synchronisation (host_out should be pinned memory);
  * complete after cfem_synchronize(). */
 int          cfem_fetch_async(cfem_problem* p, uint32_t which, double* host_out);
+/* Time-sharded problems behind ONE solver process: the decision vector, the
+ * multipliers and the results live in shared page-locked host vectors in the
+ * GLOBAL order; every rank moves only its own pieces, straight between that
+ * memory and its device arrays over its own PCIe link (asynchronous on the
+ * handle's stream; offsets and lengths in doubles).  cfem_upload_pieces marks
+ * the input as set (new x / new lambda); cfem_set_obj_factor sets sigma. */
+int          cfem_upload_pieces(cfem_problem* p, uint32_t which,
+                                const double* host_base, int32_t n,
+                                const int64_t* dev_off, const int64_t* host_off,
+                                const int64_t* len);
+int          cfem_fetch_pieces(cfem_problem* p, uint32_t which, double* host_base,
+                               int32_t n, const int64_t* dev_off,
+                               const int64_t* host_off, const int64_t* len);
+int          cfem_set_obj_factor(cfem_problem* p, double obj_factor);
 /* IPOPT-shaped conveniences: evaluate if stale, copy to host, synchronise. */
 int          cfem_eval_f(cfem_problem* p, double* f);
 int          cfem_eval_grad_f(cfem_problem* p, double* grad);

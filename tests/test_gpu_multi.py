@@ -99,3 +99,114 @@ def test_two_gpu_sharded_equals_single(mode):
     msg = out.get(timeout=10)
     assert msg == 'ok', msg
     assert all(pr.exitcode == 0 for pr in procs)
+
+
+def _solver_rank_main(rank, world, port, mode, out):
+    """Rank 0 drives the callbacks (and a whole interior-point solve) through
+    sharding.SolverFacingEvaluator; every rank moves only its own pieces."""
+    import torch
+    import torch.distributed as dist
+    from colloc_fem_code_b200 import families, nlp, sharding, synthetic
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    ev = None
+    try:
+        nx, nu, ny, N = 2, 1, 2, 30001
+        exp = synthetic.experiment(7, N, nx, nu, ny)
+        p = families.make_problem('ml', exp['y'], exp['u'], nx)
+        ev = sharding.solver_facing_evaluator(p, rank, world, device=rank,
+                                              reduce=mode)
+        if rank != 0:
+            ev.serve()
+        else:
+            assert ev.pinned
+            from oracle import ref_models
+            ref = ref_models.make_problem('ml', exp['y'], exp['u'], nx)
+            dvec, lam, sigma = synthetic.evaluation_point(p, exp)
+            for rep in range(3):
+                d = dvec * (1 + 1e-3 * rep)
+                f, g = ev.eval_fg(d)
+                np.testing.assert_allclose(f, ref.obj(d), rtol=1e-12)
+                f, grad, g, jv, hv = ev.eval_all(d, sigma, lam)
+                np.testing.assert_allclose(f, ref.obj(d), rtol=1e-12)
+                np.testing.assert_allclose(grad, ref.obj_grad(d), rtol=1e-12,
+                                           atol=1e-300)
+                scale = 1e-12 * (1 + np.abs(d).max())
+                np.testing.assert_allclose(g, ref.constr(d), rtol=1e-12,
+                                           atol=scale)
+                np.testing.assert_allclose(jv, ref.constr_jac_val(d),
+                                           rtol=1e-12, atol=1e-300)
+                np.testing.assert_allclose(hv, ref.lag_hess_val(d, sigma, lam),
+                                           rtol=1e-12, atol=1e-300)
+            hv2 = np.zeros(p.nnzhess)
+            ev.ipopt_eval(16, d, False, hv2, sigma=-0.5, lam=3 * lam)
+            np.testing.assert_allclose(hv2, ref.lag_hess_val(d, -0.5, 3 * lam),
+                                       rtol=1e-12, atol=1e-300)
+            ev.close()
+            out.put('ok')
+    except Exception as exc:            # pragma: no cover
+        out.put(f'rank {rank}: {exc!r}')
+        if rank == 0 and ev is not None:
+            try:
+                ev.stop()
+            except Exception:
+                pass
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('mode', ['peer', 'nccl'])
+def test_two_gpu_one_solver_process(mode):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_solver_rank_main,
+                         args=(r, 2, port, mode, out)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(600)
+    for pr in procs:
+        if pr.is_alive():
+            pr.kill()
+    msg = out.get(timeout=10)
+    assert msg == 'ok', msg
+    assert all(pr.exitcode == 0 for pr in procs)
+
+
+def test_one_gpu_solver_facing_pieces():
+    """world = 1: the piecewise transfers (cfem_upload_pieces /
+    cfem_fetch_pieces) against the whole-vector path of the same handle."""
+    from colloc_fem_code_b200 import backend, families, sharding, synthetic
+    nx, nu, ny, N = 5, 3, 3, 513
+    exp = synthetic.experiment(11, N, nx, nu, ny)
+    p = families.make_problem('ml_balanced', exp['y'], exp['u'], nx)
+    dvec, lam, sigma = synthetic.evaluation_point(p, exp)
+    sev = sharding.ShardedEvaluator(p, 0, 1)
+    ev = sharding.SolverFacingEvaluator(
+        p, sev.shard, sev.handle, 0, 1, broadcast=lambda box: None,
+        barrier=lambda: None, lib=sev.lib)
+    assert ev.pinned
+    f, grad, g, jv, hv = ev.eval_all(dvec, sigma, lam)
+    h = sev.handle
+    h.set_dvec(dvec)
+    h.set_multipliers(sigma, lam)
+    h.eval(backend.ALL)
+    assert f == h.fetch(backend.F)[0]
+    for bit, got in ((backend.GRAD, grad), (backend.G, g), (backend.JAC, jv),
+                     (backend.HESS, hv)):
+        np.testing.assert_array_equal(got, h.fetch(bit))
+    f2, g2 = ev.eval_fg(dvec * 1.01)
+    h.set_dvec(dvec * 1.01)
+    h.eval(backend.F | backend.G)
+    assert f2 == h.fetch(backend.F)[0]
+    np.testing.assert_array_equal(g2, h.fetch(backend.G))
+    ev.close()
