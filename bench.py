@@ -212,8 +212,15 @@ def run_reference(args, out):
 def workload_config(world, reduce_mode='none'):
     nx, nu, ny = DIMS
     how = {'skip': 'NO reduction (debug only: results incomplete)',
-           'peer': 'objective + parameter gradient reduced inside the kernel '
-                   'over NVLink peer memory (no NCCL call on the path)',
+           'peer': 'objective + parameter gradient: partial sums posted to '
+                   'every peer inside the kernel over NVLink peer memory, '
+                   'rank-order sum by a collect kernel on a side stream that '
+                   'overlaps the next step (every step is collected inside '
+                   'the timed region; no NCCL call on the path)',
+           'peer_sync': 'objective + parameter gradient reduced inside the '
+                        'kernel over NVLink peer memory, all ranks rendezvous '
+                        'at the end of every kernel (no NCCL call on the '
+                        'path)',
            'nccl': 'NCCL allreduce of objective + parameter gradient',
            'none': ''}[reduce_mode]
     return {
@@ -303,17 +310,17 @@ def run_ours(args, out):
     reduce_mode = 'none'
     if world > 1:
         reduce_mode = os.environ.get('CFEM_REDUCE', 'peer')
-        if reduce_mode == 'peer':
+        if reduce_mode in ('peer', 'peer_sync'):
             try:
-                ev.enable_peer_reduce()
+                ev.enable_peer_reduce(pipelined=reduce_mode == 'peer')
             except Exception as exc:        # no P2P / symmetric memory
                 print(f'rank {rank}: peer reduce unavailable ({exc!r}); '
                       'using NCCL', file=sys.stderr)
                 reduce_mode = 'nccl'
-        flags = torch.tensor([reduce_mode == 'peer'], dtype=torch.int32,
-                             device=f'cuda:{local_rank}')
+        flags = torch.tensor([reduce_mode.startswith('peer')],
+                             dtype=torch.int32, device=f'cuda:{local_rank}')
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-        if reduce_mode == 'peer' and int(flags.item()) == 0:
+        if reduce_mode.startswith('peer') and int(flags.item()) == 0:
             h.set_peers(0, 1, [], [])
             reduce_mode = 'nccl'
 
@@ -354,41 +361,89 @@ def run_ours(args, out):
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64,
                             device=f'cuda:{local_rank}')
+    mine = torch.tensor([sum(step_ms) / args.steps, float(np.mean(kernel_ms))],
+                        dtype=torch.float64, device=f'cuda:{local_rank}')
+    per_rank = [mine.clone() for _ in range(world)]
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_gather(per_rank, mine)
     total_ms = float(total_ms.item())
+    per_rank = {'ms_per_step': [round(float(t[0]), 5) for t in per_rank],
+                'kernel_ms': [round(float(t[1]), 5) for t in per_rank]}
 
     # ---- end to end through the host API (pinned host buffers) ---------------
-    host = backend.HostBuffers(h)
-    host.dvec[:] = ldvec
-    host.lam[:] = llam
-
-    def e2e_step(i):
-        host.dvec[0] = ldvec[0] + 1e-12 * i      # a new x every step
-        h.set_dvec(host.dvec)
-        h.set_multipliers(sigma, host.lam)
-        h.eval(backend.ALL)
-        if reduce_mode == 'nccl':
-            dist.all_reduce(red)
-            h.apply_reduced(ptrs['reduce'])
-        host.fetch_all()
-
     e2e_steps = max(3, min(args.steps, 10))
-    for i in range(2):
-        e2e_step(i)
-    sync_all()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(e2e_steps):
-        e2e_step(2 + i)
-    e1.record()
-    sync_all()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64,
-                          device=f'cuda:{local_rank}')
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_ms.item())
+    if world == 1:
+        host = backend.HostBuffers(h)
+        host.dvec[:] = ldvec
+        host.lam[:] = llam
+
+        def e2e_step(i):
+            host.dvec[0] = ldvec[0] + 1e-12 * i      # a new x every step
+            h.set_dvec(host.dvec)
+            h.set_multipliers(sigma, host.lam)
+            h.eval(backend.ALL)
+            host.fetch_all()
+
+        for i in range(2):
+            e2e_step(i)
+        sync_all()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(e2e_steps):
+            e2e_step(2 + i)
+        e1.record()
+        sync_all()
+        e2e_ms = float(e0.elapsed_time(e1))
+        e2e_h2d = int(8 * (h.ndec + h.ncons))
+        e2e_d2h = int(8 * (1 + h.ndec + h.ncons + h.nnz_jac + h.nnz_hess))
+        e2e_note = ('pinned host dvec+lambda -> H2D -> fused kernels -> D2H of '
+                    'f, grad, g, Jacobian and Hessian values; CUDA events')
+    else:
+        # ONE solver-facing process (rank 0) in front of all shards: x, lambda
+        # and the five results live in shared page-locked host vectors in the
+        # global (IPOPT) order; every rank DMAs only its own pieces over its
+        # own PCIe link (sharding.SolverFacingEvaluator).
+        hook = None
+        if reduce_mode == 'nccl':
+            def hook(handle):
+                dist.all_reduce(red)
+                handle.apply_reduced(ptrs['reduce'])
+        sfe = sharding.SolverFacingEvaluator(
+            problem, ev.shard, h, rank, world,
+            broadcast=lambda box: dist.broadcast_object_list(box, src=0),
+            barrier=dist.barrier, reduce_hook=hook, lib=ev.lib)
+        e2e_ms = 0.0
+        if rank == 0:
+            sv = sfe.sv
+            sv.dvec[:] = dvec
+            sv.lam[:] = lam
+            sv.sigma = sigma
+            request = sfe.X | sfe.LAMBDA | backend.ALL
+            for i in range(2):
+                sv.dvec[0] = dvec[0] + 1e-12 * i
+                sfe._request(request)
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                sv.dvec[0] = dvec[0] + 1e-12 * (2 + i)
+                sfe._request(request)
+            e2e_ms = 1e3 * (time.perf_counter() - t0)
+            sfe.stop()
+        else:
+            sfe.serve()
+        sync_all()
+        g = ev.shard.glob
+        # parameters / parameter-only multipliers are uploaded by every rank
+        e2e_h2d = int(8 * sum(int(pc[:, 2].sum()) for pc in sfe._in.values()))
+        e2e_d2h = int(8 * sum(int(pc[:, 2].sum()) for pc in sfe._out.values()))
+        e2e_note = ('one solver-facing process: x, lambda and results in '
+                    'shared page-locked host vectors in the global order '
+                    f'(N={g.N} samples); every rank moves its own pieces '
+                    '(H2D -> fused kernels + cross-GPU reduction -> D2H); '
+                    'host wall clock on rank 0 around complete requests; '
+                    'bytes are per rank; page-locked: ' + str(sfe.pinned))
+        sfe.close()
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -407,18 +462,15 @@ def run_ours(args, out):
             'config': workload_config(world, reduce_mode),
             'samples_per_s': value * N_PER_GPU,
             'numa_node': numa_node,
+            'per_rank': per_rank,
             'gpu_launches': int(launches),
             'wall_s_timed_region': wall,
             'clocks': clocks,
             'e2e': {
                 'value': e2e_steps * world / (e2e_ms * 1e-3), 'unit': UNIT,
-                'h2d_bytes_per_step': int(8 * (h.ndec + h.ncons)),
-                'd2h_bytes_per_step': int(8 * (1 + h.ndec + h.ncons
-                                               + h.nnz_jac + h.nnz_hess)),
+                'h2d_bytes_per_step': e2e_h2d, 'd2h_bytes_per_step': e2e_d2h,
                 'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
-                'note': 'pinned host dvec+lambda -> H2D -> fused kernels -> '
-                        'D2H of f, grad, g, Jacobian and Hessian values '
-                        '(per rank)'},
+                'note': e2e_note},
             'roofline': {
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak,

@@ -95,6 +95,7 @@ ABI = {
                                       ctypes.POINTER(ctypes.c_void_p)]),
     'cfem_peer_layout': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32,
                                         _c_int64_p, _c_int64_p]),
+    'cfem_set_peer_mode': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     'cfem_synchronize': (ctypes.c_int, [ctypes.c_void_p]),
     'cfem_event_record': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     'cfem_event_elapsed_ms': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32,
@@ -418,6 +419,12 @@ class Handle:
         fa = (ctypes.c_void_p * n)(*[int(p) for p in flag_ptrs])
         self._check(self.lib.cfem_set_peers(self._ptr, int(rank), int(world),
                                             ia, fa))
+
+    def set_peer_mode(self, pipelined):
+        """``True``: post in the kernel, collect on a side stream beside the
+        next launch (``cfem_set_peer_mode``)."""
+        self._check(self.lib.cfem_set_peer_mode(self._ptr,
+                                                1 if pipelined else 0))
 
     def apply_reduced(self, dev_ptr):
         self._check(self.lib.cfem_apply_reduced(self._ptr, int(dev_ptr)))

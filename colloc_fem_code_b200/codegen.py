@@ -659,7 +659,13 @@ class Generator:
                  f'a.reduce[b * {R} + r] = tot[r];')
         w.append('    // time-sharded run: exchange the partial sums with the peer '
                  'GPUs through NVLink-mapped memory, inside this kernel')
-        w.append(f'    if (a.peer_world > 1) cfem::peer_allreduce<{R}>(a, b, tot);')
+        w.append('    if (a.peer_world > 1) {')
+        w.append('        // pipelined mode: post only; cfem_peer_collect_kernel '
+                 'finishes the sums')
+        w.append(f'        if (a.peer_defer) {{ cfem::peer_post<{R}>(a, b, tot); '
+                 'return; }')
+        w.append(f'        cfem::peer_allreduce<{R}>(a, b, tot);')
+        w.append('    }')
         w.append(f'    if (mask & {F}u) a.f[b] = tot[0];')
         w.append(f'    if (mask & {GRAD}u) {{')
         for i, s in enumerate(self.slots[1:], start=1):
@@ -677,6 +683,25 @@ class Generator:
         for i, s in enumerate(self.slots[1:], start=1):
             w.append(f'    a.grad[b * a.ndec + a.var_off[{s["var"]}] + '
                      f'{s["flat"]}] = red[b * {R} + {i}];')
+        w.append('}')
+        w.append('')
+        w.append('// Pipelined cross-GPU reduction: waits for the posts of '
+                 'a.peer_epoch from all')
+        w.append('// ranks, sums them in rank order and writes the objective / '
+                 'parameter gradient.')
+        w.append('__global__ void cfem_peer_collect_kernel(const cfem::KArgs a, '
+                 'const unsigned mask)')
+        w.append('{')
+        w.append('    const long long b = blockIdx.x;')
+        w.append('    if (threadIdx.x != 0) return;')
+        w.append(f'    double tot[{R}];')
+        w.append(f'    cfem::peer_collect<{R}>(a, b, (long long)gridDim.x, tot);')
+        w.append(f'    if (mask & {F}u) a.f[b] = tot[0];')
+        w.append(f'    if (mask & {GRAD}u) {{')
+        for i, s in enumerate(self.slots[1:], start=1):
+            w.append(f'        a.grad[b * a.ndec + a.var_off[{s["var"]}] + '
+                     f'{s["flat"]}] = tot[{i}];')
+        w.append('    }')
         w.append('}')
         return '\n'.join(w)
 
@@ -858,6 +883,12 @@ class Generator:
                  'cudaStream_t s, const cfem::KArgs& a, const double* red)')
         w.append('{')
         w.append('    cfem_apply_reduced_kernel<<<batch, 32, 0, s>>>(a, red);')
+        w.append('    return cudaGetLastError();')
+        w.append('}')
+        w.append('static cudaError_t launch_peer_collect(unsigned mask, int batch, '
+                 'cudaStream_t s, const cfem::KArgs& a)')
+        w.append('{')
+        w.append('    cfem_peer_collect_kernel<<<batch, 32, 0, s>>>(a, mask);')
         w.append('    return cudaGetLastError();')
         w.append('}')
         w.append('}  // namespace gen')

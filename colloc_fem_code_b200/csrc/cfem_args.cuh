@@ -38,9 +38,10 @@ struct KArgs {
     unsigned int* done_count;   // [batch] groups retired per problem
     // fused cross-GPU reduction over peer memory (time-sharded runs)
     int                 peer_rank, peer_world;      // world <= 1: disabled
+    int                 peer_defer;                 // 1: post only, collect in cfem_peer_collect_kernel
     unsigned long long  peer_epoch;                 // launch counter, > 0
-    double*             peer_inbox[kMaxPeers];      // rank p's inbox  [2][world][batch*nreduce]
-    unsigned long long* peer_flag[kMaxPeers];       // rank p's flags  [2][world]
+    double*             peer_inbox[kMaxPeers];      // rank p's inbox  [kPeerRing][world][batch*nreduce]
+    unsigned long long* peer_flag[kMaxPeers];       // rank p's flags  [kPeerRing][world]
     double* reduce;         // [batch][nreduce]
     long long var_off[AtLeastOne<gen::kNumVars>::value];
     long long var_rows[AtLeastOne<gen::kNumVars>::value];

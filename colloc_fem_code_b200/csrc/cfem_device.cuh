@@ -360,17 +360,33 @@ __device__ __forceinline__ bool tree_reduce(const KArgs& a, long long b,
 // ---------------------------------------------------------------------------
 // Every rank's kernel ends with the same hand-shake, executed by thread 0 of
 // the CTA that finalises the rank's own sums (`tot`, R doubles per problem):
-//   1. store `tot` into slot [parity][my rank] of EVERY rank's inbox (peer
-//      stores through NVLink / NVSwitch-mapped memory);
+//   1. store `tot` into slot [epoch % kPeerRing][my rank] of EVERY rank's inbox
+//      (peer stores through NVLink / NVSwitch-mapped memory);
 //   2. system-scope release store of the launch epoch into the matching flag;
 //   3. spin (acquire loads) until all `world` flags of the own inbox carry the
 //      epoch, then sum the inbox rows IN RANK ORDER -- every rank computes the
 //      same bits -- and continue with the global sums.
-// No NCCL launch, no second kernel, no host round trip: the collective costs
-// two NVLink latencies.  Inboxes are double-buffered by epoch parity: a rank
-// can be at most one launch ahead of the slowest rank (it needs that rank's
-// flag of the current epoch to proceed), so two halves never collide.  All
-// ranks must issue the same sequence of launches (they do: lock-step shards).
+// No NCCL launch, no host round trip: the collective costs two NVLink
+// latencies.  Two modes (KArgs::peer_defer):
+//   synchronous  steps 1-3 inside the per-sample kernel (peer_allreduce): the
+//                kernel returns with the global sums in f / grad.
+//   pipelined    the per-sample kernel does steps 1-2 only (peer_post); step 3
+//                runs in cfem_peer_collect_kernel on a side stream and overlaps
+//                the NEXT per-sample kernel, so that ranks whose kernels finish
+//                a few microseconds apart do not wait for each other at every
+//                step.
+// Ring hazards: slot e % kPeerRing of rank p's inbox is read by p's collect of
+// epoch e and overwritten by the posts of epoch e + kPeerRing.  The host makes
+// p's per-sample kernel of epoch e + 2 wait (stream event) for p's collect of
+// epoch e; a poster of epoch E therefore first waits until every rank's flag of
+// epoch E - kPeerRing + 2 has arrived (that kernel ran => the collect of epoch
+// E - kPeerRing is complete everywhere).  With kPeerRing = 4 a rank may run two
+// steps ahead of the slowest one before it is throttled.  All ranks must issue
+// the same sequence of launches (they do: lock-step shards).  Spins are
+// bounded (kPeerSpinNs): a lost peer yields NaN sums instead of a hung GPU.
+constexpr int kPeerRing = 4;
+constexpr unsigned long long kPeerSpinNs = 20ull * 1000ull * 1000ull * 1000ull;
+
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
@@ -381,34 +397,72 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Wait until the flags of `epoch` from all ranks are in the own inbox.
+__device__ __forceinline__ bool peer_wait(const KArgs& a, unsigned long long epoch)
+{
+    const int W = a.peer_world;
+    const unsigned long long* myflag =
+        a.peer_flag[a.peer_rank] + (long long)(epoch % kPeerRing) * W;
+    const unsigned long long t0 = global_ns();
+    for (int p = 0; p < W; ++p) {
+        while (ld_acquire_sys(myflag + p) < epoch) {
+            __nanosleep(64);
+            if (global_ns() - t0 > kPeerSpinNs) return false;
+        }
+    }
+    return true;
+}
 
 template <int R>
-__device__ __forceinline__ void peer_allreduce(const KArgs& a, long long b, double (&tot)[R])
+__device__ __forceinline__ void peer_post(const KArgs& a, long long b, const double (&tot)[R])
 {
     const int W = a.peer_world, me = a.peer_rank;
     const unsigned long long epoch = a.peer_epoch;
-    const int half = (int)(epoch & 1ull);
+    const long long slot = (long long)(epoch % kPeerRing);
     const long long nb = (long long)gridDim.y;              // problems per launch
-    const long long row = ((long long)half * W + me) * nb * R + b * R;
+    if (epoch + 2 > (unsigned long long)kPeerRing)          // ring hazard (see above)
+        (void)peer_wait(a, epoch + 2 - kPeerRing);
+    const long long row = (slot * W + me) * nb * R + b * R;
     for (int p = 0; p < W; ++p) {
         double* dst = a.peer_inbox[p] + row;
 #pragma unroll
         for (int r = 0; r < R; ++r) __stcg(dst + r, tot[r]);
     }
     __threadfence_system();
-    // one flag per (parity, rank, problem) would be needed for batches; a
+    // one flag per (slot, rank, problem) would be needed for batches; a
     // time-sharded problem has batch == 1, enforced on the host
-    for (int p = 0; p < W; ++p) st_release_sys(a.peer_flag[p] + half * W + me, epoch);
-    const unsigned long long* myflag = a.peer_flag[me] + half * W;
-    for (int p = 0; p < W; ++p)
-        while (ld_acquire_sys(myflag + p) < epoch) { __nanosleep(64); }
-    const double* in = a.peer_inbox[me] + (long long)half * W * nb * R + b * R;
+    for (int p = 0; p < W; ++p) st_release_sys(a.peer_flag[p] + slot * W + me, epoch);
+}
+
+// Rank-order sum of the inbox rows of a.peer_epoch (after all flags arrived).
+template <int R>
+__device__ __forceinline__ void peer_collect(const KArgs& a, long long b, long long nb,
+                                             double (&tot)[R])
+{
+    const int W = a.peer_world;
+    const bool ok = peer_wait(a, a.peer_epoch);
+    const long long slot = (long long)(a.peer_epoch % kPeerRing);
+    const double* in = a.peer_inbox[a.peer_rank] + slot * W * nb * R + b * R;
 #pragma unroll
-    for (int r = 0; r < R; ++r) tot[r] = 0.0;
+    for (int r = 0; r < R; ++r) tot[r] = ok ? 0.0 : __longlong_as_double(0x7ff8000000000000ll);
     for (int p = 0; p < W; ++p) {
 #pragma unroll
         for (int r = 0; r < R; ++r) tot[r] += __ldcv(in + (long long)p * nb * R + r);
     }
+}
+
+template <int R>
+__device__ __forceinline__ void peer_allreduce(const KArgs& a, long long b, double (&tot)[R])
+{
+    peer_post<R>(a, b, tot);
+    peer_collect<R>(a, b, (long long)gridDim.y, tot);
 }
 
 }  // namespace cfem

@@ -25,6 +25,12 @@ struct cfem_problem {
     bool          own_stream = false;
     cudaStream_t  aux_stream = nullptr;     // parameter-only kernel, concurrent
     cudaEvent_t   ev_fork = nullptr, ev_join = nullptr;
+    // pipelined cross-GPU reduction: collect kernels on their own stream
+    cudaStream_t  peer_stream = nullptr;
+    cudaEvent_t   ev_posted = nullptr;          // per-sample kernel (with its post) enqueued
+    cudaEvent_t   ev_collect[2] = {};           // collect of epoch e -> slot e & 1
+    bool          collect_recorded[2] = {false, false};
+    int           collect_pending = -1;         // slot a consumer of f / grad must wait for
     long long     N = 0;
     int           batch = 1;
     int           halo = 0;
@@ -183,6 +189,9 @@ void cfem_destroy(cfem_problem* p)
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
+    if (p->peer_stream) { cudaStreamSynchronize(p->peer_stream); cudaStreamDestroy(p->peer_stream); }
+    if (p->ev_posted) cudaEventDestroy(p->ev_posted);
+    for (cudaEvent_t e : p->ev_collect) if (e) cudaEventDestroy(e);
     cudaFree(p->k.reduce);
     cudaFree(p->flush_buf);
     for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
@@ -264,6 +273,9 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     CFEM_TRY(cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking));
     CFEM_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     CFEM_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    CFEM_TRY(cudaStreamCreateWithFlags(&p->peer_stream, cudaStreamNonBlocking));
+    CFEM_TRY(cudaEventCreateWithFlags(&p->ev_posted, cudaEventDisableTiming));
+    for (cudaEvent_t& e : p->ev_collect) CFEM_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (cudaEvent_t& e : p->ev) CFEM_TRY(cudaEventCreate(&e));
     for (cudaEvent_t& e : p->kev) CFEM_TRY(cudaEventCreate(&e));
     CFEM_TRY(cudaMalloc(&p->d_dvec, B * L.ndec * D));
@@ -410,6 +422,13 @@ int cfem_eval(cfem_problem* p, uint32_t what)
         p->launches += 1;
     }
     const int slot = (int)(p->kev_count % cfem_problem::kTimingRing);
+    const bool posts = p->k.peer_world > 1 && (mask & (CFEM_F | CFEM_GRAD));
+    const bool pipelined = posts && p->k.peer_defer;
+    const int cslot = (int)(p->k.peer_epoch & 1ull);
+    // ring hazard of the pipelined exchange (cfem_device.cuh): this kernel
+    // must not start before the collect of two epochs ago has finished
+    if (pipelined && p->collect_recorded[cslot])
+        CFEM_CUDA(p, cudaStreamWaitEvent(p->stream, p->ev_collect[cslot], 0));
     if (p->timing) CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot], p->stream));
     CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, p->stream, p->k));
     if (p->timing) {
@@ -417,9 +436,29 @@ int cfem_eval(cfem_problem* p, uint32_t what)
         p->kev_count += 1;
     }
     p->launches += 1;
-    if (p->k.peer_world > 1 && (mask & (CFEM_F | CFEM_GRAD))) p->k.peer_epoch += 1;
+    if (pipelined) {
+        // the rank-order sum of all ranks' posts runs beside the NEXT launch
+        CFEM_CUDA(p, cudaEventRecord(p->ev_posted, p->stream));
+        CFEM_CUDA(p, cudaStreamWaitEvent(p->peer_stream, p->ev_posted, 0));
+        CFEM_CUDA(p, gen::launch_peer_collect(mask, p->batch, p->peer_stream, p->k));
+        CFEM_CUDA(p, cudaEventRecord(p->ev_collect[cslot], p->peer_stream));
+        p->collect_recorded[cslot] = true;
+        p->collect_pending = cslot;
+        p->launches += 1;
+    }
+    if (posts) p->k.peer_epoch += 1;
     if (params) CFEM_CUDA(p, cudaStreamWaitEvent(p->stream, p->ev_join, 0));
     p->valid |= mask;
+    return CFEM_OK;
+}
+
+// Pipelined cross-GPU reduction: a consumer of f / grad on the handle's stream
+// first waits for the collect kernel of the latest evaluation.
+static int cfem_join_collect(cfem_problem* p)
+{
+    if (p->collect_pending < 0) return CFEM_OK;
+    CFEM_CUDA(p, cudaStreamWaitEvent(p->stream, p->ev_collect[p->collect_pending], 0));
+    p->collect_pending = -1;
     return CFEM_OK;
 }
 
@@ -440,6 +479,7 @@ int cfem_fetch_async(cfem_problem* p, uint32_t which, double* host_out)
     if (!(p->valid & which))
         return cfem::fail(p, CFEM_ESTATE, "cfem_fetch: result not evaluated", cudaSuccess);
     CFEM_CUDA(p, cudaSetDevice(p->device));
+    if (which & (CFEM_F | CFEM_GRAD)) { int rc = cfem_join_collect(p); if (rc) return rc; }
     if (n)
         CFEM_CUDA(p, cudaMemcpyAsync(host_out, src, n * sizeof(double),
                                      cudaMemcpyDeviceToHost, p->stream));
@@ -499,6 +539,7 @@ int cfem_fetch_pieces(cfem_problem* p, uint32_t which, double* host_base,
     if (!(p->valid & which))
         return cfem::fail(p, CFEM_ESTATE, "cfem_fetch_pieces: result not evaluated", cudaSuccess);
     CFEM_CUDA(p, cudaSetDevice(p->device));
+    if (which & (CFEM_F | CFEM_GRAD)) { int rc = cfem_join_collect(p); if (rc) return rc; }
     for (int i = 0; i < n; ++i) {
         if (len[i] <= 0) continue;
         if (dev_off[i] < 0 || dev_off[i] + len[i] > cap)
@@ -574,6 +615,18 @@ int cfem_set_peers(cfem_problem* p, int32_t rank, int32_t world,
     p->k.peer_rank = rank;
     p->k.peer_world = world;
     p->k.peer_epoch = 1;        // flags start at 0
+    p->k.peer_defer = 0;
+    p->collect_recorded[0] = p->collect_recorded[1] = false;
+    p->collect_pending = -1;
+    return CFEM_OK;
+}
+
+int cfem_set_peer_mode(cfem_problem* p, int32_t pipelined)
+{
+    if (!p) return CFEM_EINVAL;
+    if (p->k.peer_world <= 1 && pipelined)
+        return cfem::fail(p, CFEM_ESTATE, "cfem_set_peer_mode: no peers set", cudaSuccess);
+    p->k.peer_defer = pipelined ? 1 : 0;
     return CFEM_OK;
 }
 
@@ -581,8 +634,8 @@ int cfem_peer_layout(const cfem_problem* p, int32_t world, int64_t* inbox_double
                      int64_t* flag_words)
 {
     if (!p || world < 1) return CFEM_EINVAL;
-    if (inbox_doubles) *inbox_doubles = 2ll * world * p->batch * gen::kNumReduce;
-    if (flag_words) *flag_words = 2ll * world;
+    if (inbox_doubles) *inbox_doubles = (long long)cfem::kPeerRing * world * p->batch * gen::kNumReduce;
+    if (flag_words) *flag_words = (long long)cfem::kPeerRing * world;
     return CFEM_OK;
 }
 
@@ -599,6 +652,7 @@ int cfem_synchronize(cfem_problem* p)
 {
     if (!p) return CFEM_EINVAL;
     CFEM_CUDA(p, cudaSetDevice(p->device));
+    { int rc = cfem_join_collect(p); if (rc) return rc; }
     CFEM_CUDA(p, cudaStreamSynchronize(p->stream));
     return CFEM_OK;
 }

@@ -222,14 +222,16 @@ class ShardedEvaluator:
             raise backend.CfemError(f'shard layout mismatch: {got} vs {want}')
         self.n_reduce = len(self.lib.model['reduce'])
 
-    def enable_peer_reduce(self, group=None):
+    def enable_peer_reduce(self, group=None, pipelined=False):
         """Switch from ``all_reduce`` + ``cfem_apply_reduced`` to the fused
         in-kernel exchange over NVLink peer memory (``cfem_set_peers``).
 
         PyTorch is only the plumbing here: a symmetric-memory allocation
         (``torch.distributed._symmetric_memory``) gives every rank a device
         pointer to every other rank's inbox; the exchange itself is done by
-        the last CTA of the per-sample kernel.
+        the last CTA of the per-sample kernel.  ``pipelined``: the kernel only
+        posts its partial sums; a collect kernel on a side stream finishes the
+        sum beside the next launch (``cfem_set_peer_mode``).
         """
         import torch
         import torch.distributed as dist
@@ -246,6 +248,7 @@ class ShardedEvaluator:
         dist.barrier(group)             # every inbox is zeroed before any store
         self.handle.set_peers(rank, world, ptrs,
                               [p + 8 * n_inbox for p in ptrs])
+        self.handle.set_peer_mode(pipelined)
         self._peer = (buf, hdl)         # keep the mapping alive
         return True
 
@@ -522,6 +525,10 @@ def solver_facing_evaluator(problem, rank, world, device=0, group=None,
     import torch
     import torch.distributed as dist
     ev = ShardedEvaluator(problem, rank, world, device=device)
+    # one explicit stream for the kernels, the copies and the NCCL calls
+    stream = torch.cuda.Stream(device=device)
+    torch.cuda.set_stream(stream)
+    ev.handle.set_stream(stream.cuda_stream)
     hook = None
     if world > 1:
         mode = reduce
@@ -554,5 +561,5 @@ def solver_facing_evaluator(problem, rank, world, device=0, group=None,
                                                          group=group),
         barrier=lambda: dist.barrier(group), reduce_hook=hook,
         lib=ev.lib)
-    out.sharded = ev
+    out.sharded, out.stream = ev, stream
     return out

@@ -173,6 +173,15 @@ int          cfem_set_peers(cfem_problem* p, int32_t rank, int32_t world,
                             void* const* inbox_ptrs, void* const* flag_ptrs);
 int          cfem_peer_layout(const cfem_problem* p, int32_t world,
                               int64_t* inbox_doubles, int64_t* flag_words);
+/* pipelined != 0: the per-sample kernel only POSTS its partial sums to the
+ * peers; a small collect kernel on a side stream waits for all ranks' posts,
+ * sums them in rank order and writes f / the parameter gradient while the next
+ * cfem_eval may already run (ranks no longer rendezvous at every step; a rank
+ * can run two evaluations ahead of the slowest one).  cfem_fetch*, the
+ * cfem_eval_* conveniences and cfem_synchronize wait for the collect; readers
+ * of the raw device pointers must call cfem_synchronize first.  Default 0:
+ * the exchange completes inside the per-sample kernel. */
+int          cfem_set_peer_mode(cfem_problem* p, int32_t pipelined);
 int          cfem_synchronize(cfem_problem* p);
 
 /* ---- measurement helpers --------------------------------------------------- */

@@ -36,12 +36,17 @@ def _rank_main(rank, world, port, mode, out):
         stream = torch.cuda.Stream(device=rank)
         torch.cuda.set_stream(stream)
         h.set_stream(stream.cuda_stream)
-        if mode == 'peer':
-            ev.enable_peer_reduce()
+        if mode.startswith('peer'):
+            ev.enable_peer_reduce(pipelined=mode == 'peer_pipelined')
         res = {}
-        for rep in range(3):                 # several epochs of the hand-shake
+        # several epochs of the hand-shake; the pipelined exchange runs ahead
+        # of its collects (ring of 4 epochs) and is only joined by a fetch
+        reps = 11 if mode == 'peer_pipelined' else 3
+        for rep in range(reps):
             ev.set_point(dvec + 1e-3 * rep, sigma, lam)
             h.eval(backend.ALL)
+            if mode == 'peer_pipelined' and rep % 4 != 3 and rep != reps - 1:
+                continue
             if mode == 'nccl':
                 ptr = h.device_ptrs()['reduce']
 
@@ -61,7 +66,7 @@ def _rank_main(rank, world, port, mode, out):
         gathered = [None] * world
         dist.gather_object(parts, gathered if rank == 0 else None, dst=0)
         if rank == 0:
-            d = dvec + 1e-3 * 2
+            d = dvec + 1e-3 * (reps - 1)
             ref = {'f': p.obj(d), 'grad': p.obj_grad(d), 'g': p.constr(d),
                    'jac': p.constr_jac_val(d),
                    'hess': p.lag_hess_val(d, sigma, lam)}
@@ -81,7 +86,7 @@ def _rank_main(rank, world, port, mode, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('mode', ['peer', 'nccl'])
+@pytest.mark.parametrize('mode', ['peer', 'peer_pipelined', 'nccl'])
 def test_two_gpu_sharded_equals_single(mode):
     import torch
     if torch.cuda.device_count() < 2:
