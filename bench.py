@@ -373,7 +373,32 @@ def run_ours(args, out):
 
     # ---- end to end through the host API (pinned host buffers) ---------------
     e2e_steps = max(3, min(args.steps, 10))
-    if world == 1:
+    sfe = None
+    if world > 1:
+        # ONE solver-facing process (rank 0) in front of all shards: x, lambda
+        # and the five results live in shared page-locked host vectors in the
+        # global (IPOPT) order; every rank DMAs only its own pieces over its
+        # own PCIe link (sharding.SolverFacingEvaluator).
+        hook = None
+        if reduce_mode == 'nccl':
+            def hook(handle):
+                dist.all_reduce(red)
+                handle.apply_reduced(ptrs['reduce'])
+        try:
+            sfe = sharding.SolverFacingEvaluator(
+                problem, ev.shard, h, rank, world,
+                broadcast=lambda box: dist.broadcast_object_list(box, src=0),
+                barrier=dist.barrier, reduce_hook=hook, lib=ev.lib)
+        except (OSError, RuntimeError, MemoryError) as exc:
+            print(f'rank {rank}: shared host vectors unavailable ({exc!r}); '
+                  'per-rank end-to-end instead', file=sys.stderr)
+        agreed = torch.tensor([sfe is not None], dtype=torch.int32,
+                              device=f'cuda:{local_rank}')
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
+        if sfe is not None and int(agreed.item()) == 0:
+            sfe.sv.close()
+            sfe = None
+    if sfe is None:
         host = backend.HostBuffers(h)
         host.dvec[:] = ldvec
         host.lam[:] = llam
@@ -383,6 +408,9 @@ def run_ours(args, out):
             h.set_dvec(host.dvec)
             h.set_multipliers(sigma, host.lam)
             h.eval(backend.ALL)
+            if reduce_mode == 'nccl':
+                dist.all_reduce(red)
+                h.apply_reduced(ptrs['reduce'])
             host.fetch_all()
 
         for i in range(2):
@@ -395,25 +423,17 @@ def run_ours(args, out):
             e2e_step(2 + i)
         e1.record()
         sync_all()
-        e2e_ms = float(e0.elapsed_time(e1))
+        e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64,
+                              device=f'cuda:{local_rank}')
+        if world > 1:
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(e2e_ms.item())
         e2e_h2d = int(8 * (h.ndec + h.ncons))
         e2e_d2h = int(8 * (1 + h.ndec + h.ncons + h.nnz_jac + h.nnz_hess))
         e2e_note = ('pinned host dvec+lambda -> H2D -> fused kernels -> D2H of '
-                    'f, grad, g, Jacobian and Hessian values; CUDA events')
+                    'f, grad, g, Jacobian and Hessian values (per rank); '
+                    'CUDA events')
     else:
-        # ONE solver-facing process (rank 0) in front of all shards: x, lambda
-        # and the five results live in shared page-locked host vectors in the
-        # global (IPOPT) order; every rank DMAs only its own pieces over its
-        # own PCIe link (sharding.SolverFacingEvaluator).
-        hook = None
-        if reduce_mode == 'nccl':
-            def hook(handle):
-                dist.all_reduce(red)
-                handle.apply_reduced(ptrs['reduce'])
-        sfe = sharding.SolverFacingEvaluator(
-            problem, ev.shard, h, rank, world,
-            broadcast=lambda box: dist.broadcast_object_list(box, src=0),
-            barrier=dist.barrier, reduce_hook=hook, lib=ev.lib)
         e2e_ms = 0.0
         if rank == 0:
             sv = sfe.sv

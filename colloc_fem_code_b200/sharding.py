@@ -283,24 +283,23 @@ class SharedVectors:
 
     def __init__(self, sizes, world, path=None):
         import mmap
-        import uuid
         self.world = world
         self.sizes = {k: int(sizes[k]) for k in self.FIELDS}
         nctrl = self._CTRL + world
         nctrl += (-nctrl) % 8                   # 64-byte aligned vectors
         total = 8 * (nctrl + sum(n + (-n) % 8 for n in self.sizes.values()))
         self.created = path is None
+        self._fd = None
         if path is None:
-            path = f'/dev/shm/cfem_{os.getpid()}_{uuid.uuid4().hex[:12]}'
-            fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
-            os.ftruncate(fd, total)
+            path, fd = self._create(total)
         else:
             fd = os.open(path, os.O_RDWR)
         self.path = path
         try:
             self._map = mmap.mmap(fd, total)
         finally:
-            os.close(fd)
+            if fd != self._fd:
+                os.close(fd)
         self.ctrl = np.frombuffer(self._map, dtype=np.int64, count=nctrl)
         self._sigma = np.frombuffer(self._map, dtype=np.float64, count=nctrl)
         off = 8 * nctrl
@@ -312,13 +311,39 @@ class SharedVectors:
         self.nbytes = total
         self._registered = None
 
+    def _create(self, total):
+        """Backing store: a tmpfs file under /dev/shm whose pages are reserved
+        up front (``posix_fallocate`` -- a too-small /dev/shm fails here with
+        ENOSPC, not later with SIGBUS); else an anonymous memfd that the other
+        ranks open through ``/proc/<pid>/fd``."""
+        import uuid
+        path = f'/dev/shm/cfem_{os.getpid()}_{uuid.uuid4().hex[:12]}'
+        try:
+            fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            try:
+                os.posix_fallocate(fd, 0, total)
+                return path, fd
+            except OSError:
+                os.close(fd)
+                os.unlink(path)
+        except OSError:
+            pass
+        fd = os.memfd_create('cfem_shared_vectors')
+        os.ftruncate(fd, total)
+        self._fd = fd                   # stays open until unlink()
+        return f'/proc/{os.getpid()}/fd/{fd}', fd
+
     def unlink(self):
         """Remove the name (the mappings stay valid); creator only."""
         if self.created and self.path:
-            try:
-                os.unlink(self.path)
-            except FileNotFoundError:
-                pass
+            if self._fd is not None:
+                os.close(self._fd)
+                self._fd = None
+            else:
+                try:
+                    os.unlink(self.path)
+                except FileNotFoundError:
+                    pass
             self.path = None
 
     def page_lock(self, lib):
@@ -377,13 +402,20 @@ class SolverFacingEvaluator:
                  'g': self.m, 'jac': shard.glob.nnz_jac,
                  'hess': shard.glob.nnz_hess}
         if rank == 0:
-            self.sv = SharedVectors(sizes, world)
+            try:
+                self.sv = SharedVectors(sizes, world)
+            except Exception:
+                broadcast([None])       # the other ranks must not hang
+                raise
             self.sv.ctrl[:] = 0
             self.sv.lam[:] = 0.0
             broadcast([self.sv.path])
         else:
             box = [None]
             broadcast(box)
+            if box[0] is None:
+                raise RuntimeError('rank 0 could not create the shared '
+                                   'host vectors')
             self.sv = SharedVectors(sizes, world, path=box[0])
         barrier()                       # everybody has mapped the segment
         self.sv.unlink()
@@ -415,13 +447,19 @@ class SolverFacingEvaluator:
                 h.fetch_pieces(bit, getattr(sv, name), self._out[name])
         h.synchronize()
 
-    @staticmethod
-    def _wait(cond):
+    TIMEOUT_S = 600.0       # a rank that died must not hang the others
+
+    @classmethod
+    def _wait(cls, cond, timeout=None):
         import time
         t0 = time.perf_counter()
         while not cond():
-            if time.perf_counter() - t0 > 2e-3:
+            waited = time.perf_counter() - t0
+            if waited > 2e-3:
                 time.sleep(1e-4)        # long host phases: stop burning a core
+            if timeout is not None and waited > timeout:
+                raise TimeoutError('time-sharded evaluation: a rank did not '
+                                   f'answer within {timeout:.0f} s')
 
     def serve(self):
         """Ranks other than 0: execute requests until the solver stops."""
@@ -447,7 +485,7 @@ class SolverFacingEvaluator:
             self._execute(request)
         ctrl[SharedVectors._CTRL] = self._seq
         done = ctrl[SharedVectors._CTRL:SharedVectors._CTRL + self.world]
-        self._wait(lambda: (done == self._seq).all())
+        self._wait(lambda: (done == self._seq).all(), self.TIMEOUT_S)
 
     def stop(self):
         if self.rank == 0 and self._seq >= 0:
