@@ -32,6 +32,8 @@ GEN_DIR = os.environ.get('CFEM_GEN_DIR') or os.path.join(HERE, '_gen')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
+LINK_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler',
+              '-fPIC']
 
 F, GRAD, G, JAC, HESS, ALL = 1, 2, 4, 8, 16, 31
 X, LAMBDA = 32, 64
@@ -97,6 +99,7 @@ ABI = {
                                         _c_int64_p, _c_int64_p]),
     'cfem_set_peer_mode': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     'cfem_synchronize': (ctypes.c_int, [ctypes.c_void_p]),
+    'cfem_set_graph_mode': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     'cfem_event_record': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     'cfem_event_elapsed_ms': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32,
                                              ctypes.c_int32,
@@ -162,23 +165,23 @@ def build_library(structure, label='model', verbose=False, files=None,
                   **gen_kwargs):
     """Generate + compile the library of ``structure``; returns the .so path.
 
-    Two translation units (``codegen.Generator.sources``) are compiled to
+    The translation unit(s) of ``codegen.Generator.sources`` are compiled to
     objects and linked; objects and the library are cached in ``GEN_DIR`` by a
     hash of their source, the hand-written files they include and the flags.
     """
     src = codegen.generate(structure, **gen_kwargs)
     flags = ' '.join(NVCC_FLAGS)
-    args_hdr = _read(os.path.join(CSRC, 'cfem_args.cuh'))
-    key_param = _digest(src['param'], args_hdr, flags)
-    key_main = _digest(src['main'], args_hdr, flags,
-                       _read(os.path.join(CSRC, 'cfem_device.cuh')),
-                       _read(os.path.join(CSRC, 'cfem_host.inl')),
-                       _read(os.path.join(INCLUDE, 'cfem.h')))
-    so_path = os.path.join(GEN_DIR, f'cfem_{label}_{key_main}{key_param}.so')
+    hand = [_read(os.path.join(CSRC, n)) for n in
+            ('cfem_args.cuh', 'cfem_device.cuh', 'cfem_host.inl')] \
+        + [_read(os.path.join(INCLUDE, 'cfem.h'))]
+    units = sorted(src)
+    keys = {u: _digest(src[u], flags, *hand) for u in units}
+    so_path = os.path.join(
+        GEN_DIR, f'cfem_{label}_' + ''.join(keys[u] for u in units) + '.so')
     if files is not None:       # every artefact this library is made of
         files.append(so_path)
-        for unit, key in (('param', key_param), ('main', key_main)):
-            stem = os.path.join(GEN_DIR, f'cfem_{label}_{unit}_{key}')
+        for unit in units:
+            stem = os.path.join(GEN_DIR, f'cfem_{label}_{unit}_{keys[unit]}')
             files += [stem + '.o', stem + '.cu']
     if os.path.isfile(so_path):
         return so_path
@@ -187,8 +190,8 @@ def build_library(structure, label='model', verbose=False, files=None,
             return so_path
         os.makedirs(GEN_DIR, exist_ok=True)
         objs = []
-        for unit, key in (('param', key_param), ('main', key_main)):
-            stem = os.path.join(GEN_DIR, f'cfem_{label}_{unit}_{key}')
+        for unit in units:
+            stem = os.path.join(GEN_DIR, f'cfem_{label}_{unit}_{keys[unit]}')
             objs.append(stem + '.o')
             if os.path.isfile(stem + '.o'):
                 continue
@@ -202,7 +205,7 @@ def build_library(structure, label='model', verbose=False, files=None,
                 print(log)
             os.replace(tmp, stem + '.o')
         tmp = f'{so_path}.tmp{os.getpid()}'
-        _nvcc(['-shared', '-o', tmp] + objs, so_path)
+        _nvcc(LINK_FLAGS + ['-shared', '-o', tmp] + objs, so_path)
         os.replace(tmp, so_path)
     return so_path
 
@@ -419,6 +422,11 @@ class Handle:
         fa = (ctypes.c_void_p * n)(*[int(p) for p in flag_ptrs])
         self._check(self.lib.cfem_set_peers(self._ptr, int(rank), int(world),
                                             ia, fa))
+
+    def set_graph_mode(self, enabled=True):
+        """One CUDA graph launch per evaluation (``cfem_set_graph_mode``)."""
+        self._check(self.lib.cfem_set_graph_mode(self._ptr,
+                                                 1 if enabled else 0))
 
     def set_peer_mode(self, pipelined):
         """``True``: post in the kernel, collect on a side stream beside the

@@ -591,9 +591,21 @@ class Generator:
             w.append('    default: break;')
             w.append('    }')
             w.append('}')
+        w.append('// Entry `e` of the parameter-only constraints (value, Jacobian '
+                 'or Hessian entry).')
+        w.append('// Launched right before the per-sample kernel on the same '
+                 'stream; the latter is')
+        w.append('// launched with programmatic stream serialisation and never '
+                 'waits on this grid')
+        w.append('// (there is no data dependence), so the two overlap without '
+                 'a second stream or')
+        w.append('// fork/join events: this kernel releases its dependents '
+                 'first thing.')
         w.append('__global__ void __launch_bounds__(64)')
-        w.append('cfem_param_kernel(const cfem::KArgs a, const unsigned mask)')
+        w.append('cfem_param_kernel(const __grid_constant__ cfem::KArgs a, '
+                 'const unsigned mask)')
         w.append('{')
+        w.append('    asm volatile("griddepcontrol.launch_dependents;");')
         w.append('    const int e = blockIdx.x * 64 + threadIdx.x;')
         w.append('    const long long b = blockIdx.y;')
         w.append(f'    if (e >= {len(order)}) return;')
@@ -613,6 +625,19 @@ class Generator:
         R = len(self.slots)
         nd = max(1, len(self.dyn_slots))
         w = []
+        w.append('// Objective / parameter-gradient entries from the reduction slots.')
+        w.append('static __device__ __forceinline__ void cfem_write_sums('
+                 f'const cfem::KArgs& a, const unsigned mask, const long long b, '
+                 f'const double (&tot)[{R}])')
+        w.append('{')
+        w.append(f'    if (mask & {F}u) a.f[b] = tot[0];')
+        w.append(f'    if (mask & {GRAD}u) {{')
+        for i, sl in enumerate(self.slots[1:], start=1):
+            w.append(f'        a.grad[b * a.ndec + a.var_off[{sl["var"]}] + '
+                     f'{sl["flat"]}] = tot[{i}];')
+        w.append('    }')
+        w.append('}')
+        w.append('')
         w.append('// Runs in the last CTA of a problem (all CFEM_TILE threads).')
         w.append('static __device__ __noinline__ void cfem_finalize('
                  'const cfem::KArgs& a, const unsigned mask, const long long b, '
@@ -660,18 +685,20 @@ class Generator:
         w.append('    // time-sharded run: exchange the partial sums with the peer '
                  'GPUs through NVLink-mapped memory, inside this kernel')
         w.append('    if (a.peer_world > 1) {')
-        w.append('        // pipelined mode: post only; cfem_peer_collect_kernel '
-                 'finishes the sums')
-        w.append(f'        if (a.peer_defer) {{ cfem::peer_post<{R}>(a, b, tot); '
-                 'return; }')
+        w.append('        if (a.peer_defer) {')
+        w.append('            // pipelined mode: finish the PREVIOUS launch, post this one')
+        w.append('            if (a.peer_epoch > 1ull && a.peer_prev_mask) {')
+        w.append(f'                double prev[{R}];')
+        w.append(f'                cfem::peer_collect<{R}>(a, b, (long long)gridDim.y, '
+                 'a.peer_epoch - 1ull, prev);')
+        w.append('                cfem_write_sums(a, a.peer_prev_mask, b, prev);')
+        w.append('            }')
+        w.append(f'            cfem::peer_post<{R}>(a, b, tot);')
+        w.append('            return;')
+        w.append('        }')
         w.append(f'        cfem::peer_allreduce<{R}>(a, b, tot);')
         w.append('    }')
-        w.append(f'    if (mask & {F}u) a.f[b] = tot[0];')
-        w.append(f'    if (mask & {GRAD}u) {{')
-        for i, s in enumerate(self.slots[1:], start=1):
-            w.append(f'        a.grad[b * a.ndec + a.var_off[{s["var"]}] + '
-                     f'{s["flat"]}] = tot[{i}];')
-        w.append('    }')
+        w.append('    cfem_write_sums(a, mask, b, tot);')
         w.append('}')
         w.append('')
         w.append('__global__ void cfem_apply_reduced_kernel(const cfem::KArgs a, '
@@ -695,13 +722,9 @@ class Generator:
         w.append('    const long long b = blockIdx.x;')
         w.append('    if (threadIdx.x != 0) return;')
         w.append(f'    double tot[{R}];')
-        w.append(f'    cfem::peer_collect<{R}>(a, b, (long long)gridDim.x, tot);')
-        w.append(f'    if (mask & {F}u) a.f[b] = tot[0];')
-        w.append(f'    if (mask & {GRAD}u) {{')
-        for i, s in enumerate(self.slots[1:], start=1):
-            w.append(f'        a.grad[b * a.ndec + a.var_off[{s["var"]}] + '
-                     f'{s["flat"]}] = tot[{i}];')
-        w.append('    }')
+        w.append(f'    cfem::peer_collect<{R}>(a, b, (long long)gridDim.x, '
+                 'a.peer_epoch, tot);')
+        w.append('    cfem_write_sums(a, mask, b, tot);')
         w.append('}')
         return '\n'.join(w)
 
@@ -780,11 +803,11 @@ class Generator:
         kernels, the reductions and the host side of the C ABI."""
         st = self.st
         kernels, smem = [], {}
+        param_kernel = self._emit_param_kernel()    # sets n_param_entries
         for m in self.masks:
             text, nbytes = self._emit_sample_kernel(m)
             kernels.append(text)
             smem[m] = nbytes
-        param_kernel = self._emit_param_kernel()
         finalize = self._emit_finalize()
         mj = json.dumps(self.model_json(), sort_keys=True)
         cstr = '\n'.join('    "' + mj[i:i + 100].replace('\\', '\\\\')
@@ -854,8 +877,9 @@ class Generator:
         w.append('}')
         w.append('// Persistent launch: at most `max_ctas` CTAs per problem '
                  '(resident CTAs per SM x SMs x waves), each looping over tiles.')
-        w.append('static cudaError_t launch_sample(unsigned mask, int batch, '
-                 'int sm_count, int waves, long long prefetch, cudaStream_t s, cfem::KArgs a)')
+        w.append('static void prepare_sample(unsigned mask, int batch, '
+                 'int sm_count, int waves, long long prefetch, '
+                 'cfem::KArgs& a, dim3& grid)')
         w.append('{')
         w.append('    int per_sm = 1;')
         w.append('    for (int i = 0; i < kNumMasks; ++i) '
@@ -870,14 +894,41 @@ class Generator:
         w.append('    if (gx < a.ntiles) a.prefetch_tiles = 0;   // persistent: cp.async double buffering instead')
         w.append('    a.ngroups = (gx + cfem::kReduceGroup - 1) / '
                  'cfem::kReduceGroup;')
-        w.append('    const dim3 grid((unsigned)gx, (unsigned)batch);')
+        w.append('    grid = dim3((unsigned)gx, (unsigned)batch);')
+        w.append('}')
+        w.append('// overlap_prev: programmatic stream serialisation -- the kernel '
+                 'may start while the')
+        w.append('// preceding kernel of the stream (the parameter-only kernel, '
+                 'no data dependence)')
+        w.append('// is still running.')
+        w.append('static cudaError_t launch_sample(unsigned mask, int batch, '
+                 'int sm_count, int waves, long long prefetch, bool overlap_prev, '
+                 'cudaStream_t s, cfem::KArgs a)')
+        w.append('{')
+        w.append('    cudaLaunchConfig_t cfg = {};')
+        w.append('    prepare_sample(mask, batch, sm_count, waves, prefetch, a, cfg.gridDim);')
+        w.append('    cfg.blockDim = dim3(CFEM_TILE);')
+        w.append('    cfg.stream = s;')
+        w.append('    cudaLaunchAttribute attr[1];')
+        w.append('    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;')
+        w.append('    attr[0].val.programmaticStreamSerializationAllowed = 1;')
+        w.append('    cfg.attrs = attr;')
+        w.append('    cfg.numAttrs = overlap_prev ? 1 : 0;')
         w.append('    switch (mask) {')
         for m in self.masks:
-            w.append(f'    case {m}u: cfem_sample_kernel_m{m}<<<grid, CFEM_TILE, '
-                     f'kSmemBytes_m{m}, s>>>(a); break;')
+            w.append(f'    case {m}u: cfg.dynamicSmemBytes = kSmemBytes_m{m}; '
+                     f'return cudaLaunchKernelEx(&cfg, cfem_sample_kernel_m{m}, a);')
         w.append('    default: return cudaErrorInvalidValue;')
         w.append('    }')
-        w.append('    return cudaGetLastError();')
+        w.append('}')
+        w.append('// for CUDA-graph kernel-node identification / updates')
+        w.append('static const void* sample_kernel_func(unsigned mask)')
+        w.append('{')
+        w.append('    switch (mask) {')
+        for m in self.masks:
+            w.append(f'    case {m}u: return (const void*)cfem_sample_kernel_m{m};')
+        w.append('    default: return nullptr;')
+        w.append('    }')
         w.append('}')
         w.append('static cudaError_t launch_apply_reduced(int batch, '
                  'cudaStream_t s, const cfem::KArgs& a, const double* red)')

@@ -38,7 +38,8 @@ struct KArgs {
     unsigned int* done_count;   // [batch] groups retired per problem
     // fused cross-GPU reduction over peer memory (time-sharded runs)
     int                 peer_rank, peer_world;      // world <= 1: disabled
-    int                 peer_defer;                 // 1: post only, collect in cfem_peer_collect_kernel
+    int                 peer_defer;                 // 1: pipelined (finish the previous epoch, post this one)
+    unsigned            peer_prev_mask;             // result mask of the previous posting launch
     unsigned long long  peer_epoch;                 // launch counter, > 0
     double*             peer_inbox[kMaxPeers];      // rank p's inbox  [kPeerRing][world][batch*nreduce]
     unsigned long long* peer_flag[kMaxPeers];       // rank p's flags  [kPeerRing][world]

@@ -370,20 +370,24 @@ __device__ __forceinline__ bool tree_reduce(const KArgs& a, long long b,
 // latencies.  Two modes (KArgs::peer_defer):
 //   synchronous  steps 1-3 inside the per-sample kernel (peer_allreduce): the
 //                kernel returns with the global sums in f / grad.
-//   pipelined    the per-sample kernel does steps 1-2 only (peer_post); step 3
-//                runs in cfem_peer_collect_kernel on a side stream and overlaps
-//                the NEXT per-sample kernel, so that ranks whose kernels finish
-//                a few microseconds apart do not wait for each other at every
-//                step.
-// Ring hazards: slot e % kPeerRing of rank p's inbox is read by p's collect of
-// epoch e and overwritten by the posts of epoch e + kPeerRing.  The host makes
-// p's per-sample kernel of epoch e + 2 wait (stream event) for p's collect of
-// epoch e; a poster of epoch E therefore first waits until every rank's flag of
-// epoch E - kPeerRing + 2 has arrived (that kernel ran => the collect of epoch
-// E - kPeerRing is complete everywhere).  With kPeerRing = 4 a rank may run two
-// steps ahead of the slowest one before it is throttled.  All ranks must issue
-// the same sequence of launches (they do: lock-step shards).  Spins are
-// bounded (kPeerSpinNs): a lost peer yields NaN sums instead of a hung GPU.
+//   pipelined    the per-sample kernel of epoch E first finishes epoch E-1
+//                (step 3 for the PREVIOUS launch -- its posts were made a whole
+//                kernel duration ago, so there is normally nothing to wait
+//                for -- and writes that launch's f / grad), then does steps 1-2
+//                for its own sums.  Ranks whose kernels finish a few
+//                microseconds apart no longer wait for each other at every
+//                step; a rank can run one launch ahead of the slowest one.
+//                The sums of the LATEST launch are finished on demand by
+//                cfem_peer_collect_kernel (before a fetch / synchronise).
+// Ring hazards: slot e % kPeerRing of rank p's inbox is read by p's collects of
+// epoch e (inside p's kernel of epoch e+1 and/or in a collect kernel that is
+// stream-ordered before it) and overwritten by the posts of epoch
+// e + kPeerRing, which a rank makes only after it has seen every rank's flag
+// of epoch e + kPeerRing - 1 (pipelined) or e + kPeerRing - 1 completed
+// in-kernel (synchronous): p's kernel of epoch e+1 is long finished then.
+// All ranks must issue the same sequence of launches (they do: lock-step
+// shards).  Spins are bounded (kPeerSpinNs): a lost peer yields NaN sums
+// instead of a hung GPU.
 constexpr int kPeerRing = 4;
 constexpr unsigned long long kPeerSpinNs = 20ull * 1000ull * 1000ull * 1000ull;
 
@@ -427,8 +431,6 @@ __device__ __forceinline__ void peer_post(const KArgs& a, long long b, const dou
     const unsigned long long epoch = a.peer_epoch;
     const long long slot = (long long)(epoch % kPeerRing);
     const long long nb = (long long)gridDim.y;              // problems per launch
-    if (epoch + 2 > (unsigned long long)kPeerRing)          // ring hazard (see above)
-        (void)peer_wait(a, epoch + 2 - kPeerRing);
     const long long row = (slot * W + me) * nb * R + b * R;
     for (int p = 0; p < W; ++p) {
         double* dst = a.peer_inbox[p] + row;
@@ -441,14 +443,14 @@ __device__ __forceinline__ void peer_post(const KArgs& a, long long b, const dou
     for (int p = 0; p < W; ++p) st_release_sys(a.peer_flag[p] + slot * W + me, epoch);
 }
 
-// Rank-order sum of the inbox rows of a.peer_epoch (after all flags arrived).
+// Rank-order sum of the inbox rows of `epoch` (after all flags arrived).
 template <int R>
 __device__ __forceinline__ void peer_collect(const KArgs& a, long long b, long long nb,
-                                             double (&tot)[R])
+                                             unsigned long long epoch, double (&tot)[R])
 {
     const int W = a.peer_world;
-    const bool ok = peer_wait(a, a.peer_epoch);
-    const long long slot = (long long)(a.peer_epoch % kPeerRing);
+    const bool ok = peer_wait(a, epoch);
+    const long long slot = (long long)(epoch % kPeerRing);
     const double* in = a.peer_inbox[a.peer_rank] + slot * W * nb * R + b * R;
 #pragma unroll
     for (int r = 0; r < R; ++r) tot[r] = ok ? 0.0 : __longlong_as_double(0x7ff8000000000000ll);
@@ -462,7 +464,7 @@ template <int R>
 __device__ __forceinline__ void peer_allreduce(const KArgs& a, long long b, double (&tot)[R])
 {
     peer_post<R>(a, b, tot);
-    peer_collect<R>(a, b, (long long)gridDim.y, tot);
+    peer_collect<R>(a, b, (long long)gridDim.y, a.peer_epoch, tot);
 }
 
 }  // namespace cfem

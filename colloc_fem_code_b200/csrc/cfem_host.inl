@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "cfem.h"
 
@@ -25,12 +26,24 @@ struct cfem_problem {
     bool          own_stream = false;
     cudaStream_t  aux_stream = nullptr;     // parameter-only kernel, concurrent
     cudaEvent_t   ev_fork = nullptr, ev_join = nullptr;
-    // pipelined cross-GPU reduction: collect kernels on their own stream
-    cudaStream_t  peer_stream = nullptr;
-    cudaEvent_t   ev_posted = nullptr;          // per-sample kernel (with its post) enqueued
-    cudaEvent_t   ev_collect[2] = {};           // collect of epoch e -> slot e & 1
-    bool          collect_recorded[2] = {false, false};
-    int           collect_pending = -1;         // slot a consumer of f / grad must wait for
+    // pipelined cross-GPU reduction: the sums of the latest posting launch are
+    // finished on demand (cfem_peer_collect_kernel) before f / grad are consumed
+    bool          collect_pending = false;
+    unsigned long long collect_epoch = 0;
+    unsigned      collect_mask = 0;
+    // CUDA graph of one evaluation (parameter-only kernel || per-sample kernel)
+    struct StepGraph {
+        cudaGraph_t     graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaGraphNode_t k1 = nullptr, k2 = nullptr;
+        cudaKernelNodeParams p1{}, p2{};
+        cfem::KArgs     a1{}, a2{};     // kernel arguments currently baked into exec
+        bool            params = false;
+    };
+    StepGraph     graphs[gen::kNumMasks];
+    bool          use_graph = false;            // cfem_set_graph_mode / CFEM_GRAPH
+    bool          use_pdl = true;               // overlap the two kernels by programmatic dependent launch (CFEM_PDL)
+    bool          skip_param = false;           // CFEM_SKIP_PARAM: step-overhead experiments only (results incomplete)
     long long     N = 0;
     int           batch = 1;
     int           halo = 0;
@@ -188,10 +201,11 @@ void cfem_destroy(cfem_problem* p)
     cudaFree(p->k.gpartials);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
+    for (auto& g : p->graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
     if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
-    if (p->peer_stream) { cudaStreamSynchronize(p->peer_stream); cudaStreamDestroy(p->peer_stream); }
-    if (p->ev_posted) cudaEventDestroy(p->ev_posted);
-    for (cudaEvent_t e : p->ev_collect) if (e) cudaEventDestroy(e);
     cudaFree(p->k.reduce);
     cudaFree(p->flush_buf);
     for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
@@ -233,6 +247,9 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     p->sm_count = sm_count;
     if (const char* w = getenv("CFEM_WAVES")) { p->waves = atoi(w) > 0 ? atoi(w) : 1; }
     if (const char* w = getenv("CFEM_PREFETCH")) { p->prefetch = atoll(w); }
+    if (const char* w = getenv("CFEM_PDL")) { p->use_pdl = atoi(w) != 0; }
+    if (const char* w = getenv("CFEM_GRAPH")) { p->use_graph = atoi(w) != 0; }
+    if (const char* w = getenv("CFEM_SKIP_PARAM")) { p->skip_param = atoi(w) != 0; }   // measurement only
     p->N = n_samples;
     p->batch = batch;
     p->halo = halo;
@@ -273,9 +290,6 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     CFEM_TRY(cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking));
     CFEM_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     CFEM_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
-    CFEM_TRY(cudaStreamCreateWithFlags(&p->peer_stream, cudaStreamNonBlocking));
-    CFEM_TRY(cudaEventCreateWithFlags(&p->ev_posted, cudaEventDisableTiming));
-    for (cudaEvent_t& e : p->ev_collect) CFEM_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (cudaEvent_t& e : p->ev) CFEM_TRY(cudaEventCreate(&e));
     for (cudaEvent_t& e : p->kev) CFEM_TRY(cudaEventCreate(&e));
     CFEM_TRY(cudaMalloc(&p->d_dvec, B * L.ndec * D));
@@ -400,6 +414,87 @@ int cfem_set_multipliers_device(cfem_problem* p, double obj_factor, const double
     return CFEM_OK;
 }
 
+// One evaluation as a CUDA graph: captured once per kernel variant from the
+// same enqueue sequence (fork -> parameter-only kernel on the auxiliary stream,
+// per-sample kernel, join), then re-launched with the kernel arguments of the
+// two kernel nodes updated in place whenever they changed (new input pointers,
+// obj_factor, peer epoch).  Saves the stream-event bookkeeping between the
+// launches, which matters at the scripts' native lengths (launch-bound).
+static int cfem_launch_graph(cfem_problem* p, unsigned mask, bool params)
+{
+    int idx = -1;
+    for (int i = 0; i < gen::kNumMasks; ++i) if (gen::kMasks[i] == mask) idx = i;
+    if (idx < 0) return cfem::fail(p, CFEM_EINVAL, "cfem_eval: no graph slot for this kernel", cudaSuccess);
+    cfem_problem::StepGraph& g = p->graphs[idx];
+    cfem::KArgs a1 = p->k;
+    dim3 grid;
+    gen::prepare_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, a1, grid);
+    if (g.exec && g.params != params) {         // CFEM_SKIP_PARAM toggled: rebuild
+        cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph);
+        g = cfem_problem::StepGraph();
+    }
+    if (!g.exec) {
+        CFEM_CUDA(p, cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = cudaSuccess;
+        if (params) {
+            e = cudaEventRecord(p->ev_fork, p->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(p->aux_stream, p->ev_fork, 0);
+            if (e == cudaSuccess) e = gen::launch_param(mask, p->batch, p->aux_stream, p->k);
+            if (e == cudaSuccess) e = cudaEventRecord(p->ev_join, p->aux_stream);
+        }
+        if (e == cudaSuccess)
+            e = gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, false, p->stream, p->k);
+        if (e == cudaSuccess && params) e = cudaStreamWaitEvent(p->stream, p->ev_join, 0);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e2 = cudaStreamEndCapture(p->stream, &graph);
+        if (e != cudaSuccess || e2 != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return cfem::fail(p, CFEM_ECUDA, "cfem_eval: graph capture failed", e != cudaSuccess ? e : e2);
+        }
+        g.graph = graph;
+        size_t n = 0;
+        CFEM_CUDA(p, cudaGraphGetNodes(graph, nullptr, &n));
+        std::vector<cudaGraphNode_t> nodes(n);
+        CFEM_CUDA(p, cudaGraphGetNodes(graph, nodes.data(), &n));
+        const void* f1 = gen::sample_kernel_func(mask);
+        for (cudaGraphNode_t node : nodes) {
+            cudaGraphNodeType type;
+            CFEM_CUDA(p, cudaGraphNodeGetType(node, &type));
+            if (type != cudaGraphNodeTypeKernel) continue;
+            cudaKernelNodeParams kp{};
+            CFEM_CUDA(p, cudaGraphKernelNodeGetParams(node, &kp));
+            if (kp.func == f1) { g.k1 = node; g.p1 = kp; }
+            else               { g.k2 = node; g.p2 = kp; }
+        }
+        if (!g.k1 || (params && !g.k2))
+            return cfem::fail(p, CFEM_ECUDA, "cfem_eval: kernel nodes not found in the captured graph", cudaSuccess);
+        CFEM_CUDA(p, cudaGraphInstantiate(&g.exec, g.graph, 0));
+        g.a1 = a1;
+        g.a2 = p->k;
+        g.params = params;
+    } else {
+        if (memcmp(&g.a1, &a1, sizeof(cfem::KArgs)) != 0) {
+            g.a1 = a1;
+            void* args[1] = {&g.a1};
+            cudaKernelNodeParams kp = g.p1;
+            kp.kernelParams = args;
+            kp.extra = nullptr;
+            CFEM_CUDA(p, cudaGraphExecKernelNodeSetParams(g.exec, g.k1, &kp));
+        }
+        if (params && memcmp(&g.a2, &p->k, sizeof(cfem::KArgs)) != 0) {
+            g.a2 = p->k;
+            unsigned m = mask;
+            void* args[2] = {&g.a2, &m};
+            cudaKernelNodeParams kp = g.p2;
+            kp.kernelParams = args;
+            kp.extra = nullptr;
+            CFEM_CUDA(p, cudaGraphExecKernelNodeSetParams(g.exec, g.k2, &kp));
+        }
+    }
+    CFEM_CUDA(p, cudaGraphLaunch(g.exec, p->stream));
+    return CFEM_OK;
+}
+
 int cfem_eval(cfem_problem* p, uint32_t what)
 {
     if (!p || what == 0 || (what & ~CFEM_ALL)) return CFEM_EINVAL;
@@ -412,42 +507,47 @@ int cfem_eval(cfem_problem* p, uint32_t what)
     CFEM_CUDA(p, cudaSetDevice(p->device));
     // The parameter-only functions are independent of the per-sample pass:
     // fork them onto the auxiliary stream so that they overlap it.
-    const bool params = gen::kNumParamEntries > 0 &&
+    const bool params = gen::kNumParamEntries > 0 && !p->skip_param &&
                         (mask & (CFEM_G | CFEM_JAC | CFEM_HESS));
-    if (params) {
-        CFEM_CUDA(p, cudaEventRecord(p->ev_fork, p->stream));
-        CFEM_CUDA(p, cudaStreamWaitEvent(p->aux_stream, p->ev_fork, 0));
-        CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->aux_stream, p->k));
-        CFEM_CUDA(p, cudaEventRecord(p->ev_join, p->aux_stream));
-        p->launches += 1;
-    }
     const int slot = (int)(p->kev_count % cfem_problem::kTimingRing);
     const bool posts = p->k.peer_world > 1 && (mask & (CFEM_F | CFEM_GRAD));
     const bool pipelined = posts && p->k.peer_defer;
-    const int cslot = (int)(p->k.peer_epoch & 1ull);
-    // ring hazard of the pipelined exchange (cfem_device.cuh): this kernel
-    // must not start before the collect of two epochs ago has finished
-    if (pipelined && p->collect_recorded[cslot])
-        CFEM_CUDA(p, cudaStreamWaitEvent(p->stream, p->ev_collect[cslot], 0));
-    if (p->timing) CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot], p->stream));
-    CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, p->stream, p->k));
-    if (p->timing) {
-        CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot + 1], p->stream));
-        p->kev_count += 1;
+    if (p->use_graph && !p->timing) {
+        // one graph launch: both kernels as parallel nodes, no stream events
+        int rc = cfem_launch_graph(p, mask, params);
+        if (rc) return rc;
+    } else if (params && p->use_pdl && !p->timing) {
+        // Both kernels on ONE stream, no events: the parameter-only kernel
+        // releases its dependents at once (griddepcontrol.launch_dependents),
+        // the per-sample kernel is launched with programmatic stream
+        // serialisation and never waits on it -- they overlap.
+        CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->stream, p->k));
+        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, true, p->stream, p->k));
+    } else {
+        if (params) {
+            CFEM_CUDA(p, cudaEventRecord(p->ev_fork, p->stream));
+            CFEM_CUDA(p, cudaStreamWaitEvent(p->aux_stream, p->ev_fork, 0));
+            CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->aux_stream, p->k));
+            CFEM_CUDA(p, cudaEventRecord(p->ev_join, p->aux_stream));
+        }
+        if (p->timing) CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot], p->stream));
+        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, false, p->stream, p->k));
+        if (p->timing) {
+            CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot + 1], p->stream));
+            p->kev_count += 1;
+        }
+        if (params) CFEM_CUDA(p, cudaStreamWaitEvent(p->stream, p->ev_join, 0));
     }
-    p->launches += 1;
-    if (pipelined) {
-        // the rank-order sum of all ranks' posts runs beside the NEXT launch
-        CFEM_CUDA(p, cudaEventRecord(p->ev_posted, p->stream));
-        CFEM_CUDA(p, cudaStreamWaitEvent(p->peer_stream, p->ev_posted, 0));
-        CFEM_CUDA(p, gen::launch_peer_collect(mask, p->batch, p->peer_stream, p->k));
-        CFEM_CUDA(p, cudaEventRecord(p->ev_collect[cslot], p->peer_stream));
-        p->collect_recorded[cslot] = true;
-        p->collect_pending = cslot;
-        p->launches += 1;
+    p->launches += params ? 2 : 1;
+    if (posts) {
+        // pipelined: this launch only posted its sums; whoever consumes f / grad
+        // first finishes them (cfem_join_collect); else the next launch does
+        p->collect_pending = pipelined;
+        p->collect_epoch = p->k.peer_epoch;
+        p->collect_mask = mask;
+        p->k.peer_prev_mask = mask;
     }
     if (posts) p->k.peer_epoch += 1;
-    if (params) CFEM_CUDA(p, cudaStreamWaitEvent(p->stream, p->ev_join, 0));
     p->valid |= mask;
     return CFEM_OK;
 }
@@ -456,9 +556,12 @@ int cfem_eval(cfem_problem* p, uint32_t what)
 // first waits for the collect kernel of the latest evaluation.
 static int cfem_join_collect(cfem_problem* p)
 {
-    if (p->collect_pending < 0) return CFEM_OK;
-    CFEM_CUDA(p, cudaStreamWaitEvent(p->stream, p->ev_collect[p->collect_pending], 0));
-    p->collect_pending = -1;
+    if (!p->collect_pending) return CFEM_OK;
+    cfem::KArgs a = p->k;
+    a.peer_epoch = p->collect_epoch;
+    CFEM_CUDA(p, gen::launch_peer_collect(p->collect_mask, p->batch, p->stream, a));
+    p->launches += 1;
+    p->collect_pending = false;
     return CFEM_OK;
 }
 
@@ -616,8 +719,15 @@ int cfem_set_peers(cfem_problem* p, int32_t rank, int32_t world,
     p->k.peer_world = world;
     p->k.peer_epoch = 1;        // flags start at 0
     p->k.peer_defer = 0;
-    p->collect_recorded[0] = p->collect_recorded[1] = false;
-    p->collect_pending = -1;
+    p->k.peer_prev_mask = 0;
+    p->collect_pending = false;
+    return CFEM_OK;
+}
+
+int cfem_set_graph_mode(cfem_problem* p, int32_t enabled)
+{
+    if (!p) return CFEM_EINVAL;
+    p->use_graph = enabled != 0;
     return CFEM_OK;
 }
 
@@ -626,6 +736,8 @@ int cfem_set_peer_mode(cfem_problem* p, int32_t pipelined)
     if (!p) return CFEM_EINVAL;
     if (p->k.peer_world <= 1 && pipelined)
         return cfem::fail(p, CFEM_ESTATE, "cfem_set_peer_mode: no peers set", cudaSuccess);
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    { int rc = cfem_join_collect(p); if (rc) return rc; }
     p->k.peer_defer = pipelined ? 1 : 0;
     return CFEM_OK;
 }

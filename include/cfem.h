@@ -173,16 +173,23 @@ int          cfem_set_peers(cfem_problem* p, int32_t rank, int32_t world,
                             void* const* inbox_ptrs, void* const* flag_ptrs);
 int          cfem_peer_layout(const cfem_problem* p, int32_t world,
                               int64_t* inbox_doubles, int64_t* flag_words);
-/* pipelined != 0: the per-sample kernel only POSTS its partial sums to the
- * peers; a small collect kernel on a side stream waits for all ranks' posts,
- * sums them in rank order and writes f / the parameter gradient while the next
- * cfem_eval may already run (ranks no longer rendezvous at every step; a rank
- * can run two evaluations ahead of the slowest one).  cfem_fetch*, the
- * cfem_eval_* conveniences and cfem_synchronize wait for the collect; readers
- * of the raw device pointers must call cfem_synchronize first.  Default 0:
- * the exchange completes inside the per-sample kernel. */
+/* pipelined != 0: the per-sample kernel POSTS its partial sums to the peers
+ * and, instead of waiting for theirs, finishes the sums of the PREVIOUS launch
+ * (posted a whole kernel duration ago); ranks no longer rendezvous at every
+ * step and a rank can run one evaluation ahead of the slowest one.  The sums
+ * of the latest launch are finished on demand by a small collect kernel:
+ * cfem_fetch*, the cfem_eval_* conveniences and cfem_synchronize launch it;
+ * readers of the raw device pointers must call cfem_synchronize first.
+ * Default 0: the exchange completes inside the per-sample kernel. */
 int          cfem_set_peer_mode(cfem_problem* p, int32_t pipelined);
 int          cfem_synchronize(cfem_problem* p);
+/* enabled != 0: cfem_eval launches ONE CUDA graph per evaluation (the
+ * parameter-only kernel and the per-sample kernel as parallel nodes, captured
+ * once per kernel variant, kernel arguments updated in place) instead of two
+ * kernel launches with fork/join events -- for the launch-bound native
+ * trajectory lengths.  Ignored while cfem_set_kernel_timing is on (the timing
+ * events live between the launches).  Default: environment CFEM_GRAPH, else 0. */
+int          cfem_set_graph_mode(cfem_problem* p, int32_t enabled);
 
 /* ---- measurement helpers --------------------------------------------------- */
 /* CUDA events on the handle's stream (slot 0..15). */

@@ -295,3 +295,59 @@ def test_reductions_are_bitwise_reproducible():
         grad = h.fetch(backend.GRAD).tobytes()
         seen.add((f, grad))
     assert len(seen) == 1
+
+
+@pytest.mark.parametrize('kind,dims,N,batch', [
+    ('ml_balanced', (5, 3, 3), 250, 3), ('ndisc_zoh', (4, 2, 7), 601, 1),
+    ('ml', (2, 1, 2), 70_001, 1)])
+def test_launch_variants_give_identical_bits(kind, dims, N, batch, monkeypatch):
+    """The two kernels of a callback set overlapped by programmatic dependent
+    launch on one stream (default), forked/joined over an auxiliary stream
+    (CFEM_PDL=0) and the CUDA-graph form of the latter (CFEM_GRAPH=1) are the
+    same arithmetic: results must agree bit for bit, for every callback
+    subset."""
+    nx, nu, ny = dims
+    cases = []
+    for b in range(batch):
+        exp = synthetic.experiment(40 + b, N, nx, nu, ny)
+        p = families.make_problem(kind, exp['y'], exp['u'], nx, dt=0.05)
+        cases.append((p,) + synthetic.evaluation_point(p, exp, seed=b))
+    st = cases[0][0].structure
+    lib = backend.Library.for_structure(st)
+    data = [np.stack([c[0].structure.data[i]['source'] for c in cases])
+            for i in range(len(st.data))]
+    if batch == 1:
+        data = [d[0] for d in data]
+    dvec = np.stack([c[1] for c in cases])
+    lam = np.stack([c[2] for c in cases])
+    results = {}
+    for label, env in (('pdl', {}),
+                       ('fork-join', {'CFEM_PDL': '0'}),
+                       ('graph', {'CFEM_PDL': '0', 'CFEM_GRAPH': '1'})):
+        for k in ('CFEM_PDL', 'CFEM_GRAPH'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        h = backend.Handle(lib, N, data, st.scalar_values, batch=batch)
+        got = []
+        for rep, mask in enumerate((backend.ALL, backend.F | backend.G,
+                                    backend.HESS, backend.JAC, backend.ALL)):
+            h.set_dvec(dvec * (1 + 1e-3 * rep))
+            h.set_multipliers(0.5 + rep, lam)       # new kernel arguments
+            h.eval(mask)
+            for bit in (1, 2, 4, 8, 16):
+                if mask & bit:
+                    got.append(h.fetch(bit).copy())
+        results[label] = got
+        h.close()
+    for label in ('fork-join', 'graph'):
+        for a, b in zip(results['pdl'], results[label]):
+            np.testing.assert_array_equal(a, b, err_msg=label)
+    # and against the oracle-checked single-problem path
+    p, d0, l0, _ = cases[0]
+    one = p.backend.eval_all(d0 * (1 + 4e-3), 4.5, l0)
+    last = results['pdl'][-5:]
+    for a, b in zip(last, one):
+        np.testing.assert_array_equal(np.ravel(np.asarray(a))[:np.size(b)]
+                                      if batch > 1 else np.ravel(a),
+                                      np.ravel(b))
