@@ -293,7 +293,6 @@ class Generator:
             off += _skew_size(core, s['nrows'])
         off += off & 1
         stage_size = off - stage_off
-        off += stage_size           # staging buffer 1 (prefetch target)
         # output passes: group the items of every function under the budget
         wbuf = 0
         for p in plan:
@@ -321,9 +320,17 @@ class Generator:
         off += off & 1
         wbuf_off = off
         off += warps * wbuf
+        # staging buffer 1 (target of the next tile's cp.async) comes LAST: a
+        # launch in which every CTA has exactly one tile never touches it and
+        # is made with `total_single` bytes of dynamic shared memory only
+        off += off & 1
+        stage1_off = off
+        off += stage_size
         return {'param_off': param_off, 'stor': stor, 'red_off': red_off,
                 'wbuf_off': wbuf_off, 'wbuf': wbuf, 'total': off,
+                'total_single': stage1_off,
                 'stage_off': stage_off, 'stage_size': stage_size,
+                'stage_stride': stage1_off - stage_off,
                 'pat_off': pat_off}
 
     # ------------------------------------------------------------------
@@ -339,6 +346,8 @@ class Generator:
             n for n, bit in (('F', F), ('GRAD', GRAD), ('G', G), ('JAC', JAC),
                              ('HESS', HESS)) if mask & bit))
         w.append(f'constexpr size_t kSmemBytes_m{mask} = {lay["total"] * 8};')
+        w.append(f'constexpr size_t kSmemBytes1_m{mask} = '
+                 f'{lay["total_single"] * 8};   // one tile per CTA')
         bounds = f'{T}, {self.min_blocks}' if self.min_blocks else f'{T}'
         w.append(f'__global__ void __launch_bounds__({bounds})')
         w.append(f'cfem_sample_kernel_m{mask}(const __grid_constant__ cfem::KArgs a)')
@@ -380,7 +389,7 @@ class Generator:
             """cp.async of one tile's rows into staging buffer buf_expr."""
             out = ['        {',
                    f'            double* const stg = smem + '
-                   f'{lay["stage_off"]} + ({buf_expr}) * {lay["stage_size"]};',
+                   f'{lay["stage_off"]} + ({buf_expr}) * {lay["stage_stride"]};',
                    f'            const long long r0 = ({tile_expr}) * {T};',
                    '            (void)stg; (void)r0;']
             for key in sorted(lay['stor']):
@@ -441,7 +450,7 @@ class Generator:
         w.append('    cfem::cp_async_wait<1>();      // this tile has landed')
         w.append('    __syncthreads();')
         w.append(f'    double* const stg = smem + {lay["stage_off"]} + buf * '
-                 f'{lay["stage_size"]};')
+                 f'{lay["stage_stride"]};')
         w.append(f'    const long long k0 = tile * {T};')
         w.append('    const long long kw = k0 + warp * 32;')
         w.append('    const long long k = k0 + tid;')
@@ -859,6 +868,14 @@ class Generator:
         w.append(f'constexpr int kNumParamEntries = {self.n_param_entries};')
         w.append(launch_param_sig + ';    // parameter-only unit')
         w.append(f'static int g_ctas_per_sm[{len(self.masks)}];')
+        w.append(f'static int g_ctas_per_sm1[{len(self.masks)}];   '
+                 '// with the single-buffer shared-memory size')
+        w.append('static bool g_single_buf = true;      // CFEM_SINGLE_BUF=0: '
+                 'always both staging buffers')
+        w.append('static const size_t kSmem2[] = {'
+                 + ', '.join(f'kSmemBytes_m{m}' for m in self.masks) + '};')
+        w.append('static const size_t kSmem1[] = {'
+                 + ', '.join(f'kSmemBytes1_m{m}' for m in self.masks) + '};')
         w.append('static cudaError_t configure_kernels()')
         w.append('{')
         w.append('    cudaError_t e = cudaSuccess;')
@@ -873,18 +890,37 @@ class Generator:
                      f'kSmemBytes_m{m});')
             w.append('    if (e != cudaSuccess) return e;')
             w.append(f'    if (g_ctas_per_sm[{i}] < 1) g_ctas_per_sm[{i}] = 1;')
+            w.append('    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor('
+                     f'&g_ctas_per_sm1[{i}], cfem_sample_kernel_m{m}, CFEM_TILE, '
+                     f'kSmemBytes1_m{m});')
+            w.append('    if (e != cudaSuccess) return e;')
+            w.append(f'    if (g_ctas_per_sm1[{i}] < 1) g_ctas_per_sm1[{i}] = 1;')
+        w.append('    if (const char* v = getenv("CFEM_SINGLE_BUF")) '
+                 'g_single_buf = atoi(v) != 0;')
         w.append('    return e;')
         w.append('}')
         w.append('// Persistent launch: at most `max_ctas` CTAs per problem '
                  '(resident CTAs per SM x SMs x waves), each looping over tiles.')
+        w.append('// When that covers every tile (one tile per CTA) the second '
+                 'staging buffer is')
+        w.append('// not allocated: less shared memory per CTA, more resident '
+                 'CTAs per SM.')
         w.append('static void prepare_sample(unsigned mask, int batch, '
                  'int sm_count, int waves, long long prefetch, '
-                 'cfem::KArgs& a, dim3& grid)')
+                 'cfem::KArgs& a, dim3& grid, size_t& smem)')
         w.append('{')
-        w.append('    int per_sm = 1;')
+        w.append('    int idx = 0;')
         w.append('    for (int i = 0; i < kNumMasks; ++i) '
-                 'if (kMasks[i] == mask) per_sm = g_ctas_per_sm[i];')
+                 'if (kMasks[i] == mask) idx = i;')
+        w.append('    int per_sm = g_ctas_per_sm1[idx];')
         w.append('    long long gx = (long long)per_sm * sm_count * waves / batch;')
+        w.append('    smem = kSmem1[idx];')
+        w.append('    if (!g_single_buf || gx < a.ntiles) {     '
+                 '// persistent CTAs: double buffering')
+        w.append('        per_sm = g_ctas_per_sm[idx];')
+        w.append('        gx = (long long)per_sm * sm_count * waves / batch;')
+        w.append('        smem = kSmem2[idx];')
+        w.append('    }')
         w.append('    if (gx < 1) gx = 1;')
         w.append('    if (gx > a.ntiles) gx = a.ntiles;')
         w.append('    a.nctas = gx;')
@@ -906,7 +942,9 @@ class Generator:
                  'cudaStream_t s, cfem::KArgs a)')
         w.append('{')
         w.append('    cudaLaunchConfig_t cfg = {};')
-        w.append('    prepare_sample(mask, batch, sm_count, waves, prefetch, a, cfg.gridDim);')
+        w.append('    size_t smem = 0;')
+        w.append('    prepare_sample(mask, batch, sm_count, waves, prefetch, a, cfg.gridDim, smem);')
+        w.append('    cfg.dynamicSmemBytes = smem;')
         w.append('    cfg.blockDim = dim3(CFEM_TILE);')
         w.append('    cfg.stream = s;')
         w.append('    cudaLaunchAttribute attr[1];')
@@ -916,7 +954,7 @@ class Generator:
         w.append('    cfg.numAttrs = overlap_prev ? 1 : 0;')
         w.append('    switch (mask) {')
         for m in self.masks:
-            w.append(f'    case {m}u: cfg.dynamicSmemBytes = kSmemBytes_m{m}; '
+            w.append(f'    case {m}u: '
                      f'return cudaLaunchKernelEx(&cfg, cfem_sample_kernel_m{m}, a);')
         w.append('    default: return cudaErrorInvalidValue;')
         w.append('    }')

@@ -428,7 +428,8 @@ static int cfem_launch_graph(cfem_problem* p, unsigned mask, bool params)
     cfem_problem::StepGraph& g = p->graphs[idx];
     cfem::KArgs a1 = p->k;
     dim3 grid;
-    gen::prepare_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, a1, grid);
+    size_t smem = 0;
+    gen::prepare_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, a1, grid, smem);
     if (g.exec && g.params != params) {         // CFEM_SKIP_PARAM toggled: rebuild
         cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph);
         g = cfem_problem::StepGraph();

@@ -21,10 +21,17 @@ KIND = os.environ.get('SWEEP_KIND', 'ml')
 DIMS = tuple(int(c) for c in os.environ.get('SWEEP_DIMS', '212'))
 N = int(os.environ.get('SWEEP_N', 1_000_000))
 VARIANTS = []
-for st_ in (None, 'wb', 'cg'):
-    VARIANTS.append(dict(tile=128, pass_budget=6, store=st_))
-    VARIANTS.append(dict(tile=128, pass_budget=6, store=st_,
-                         experiment='noload'))
+if os.environ.get('SWEEP_SET', 'occupancy') == 'store':
+    for st_ in (None, 'wb', 'cg'):
+        VARIANTS.append(dict(tile=128, pass_budget=6, store=st_))
+        VARIANTS.append(dict(tile=128, pass_budget=6, store=st_,
+                             experiment='noload'))
+else:       # resident CTAs per SM: launch bounds x single staging buffer
+    for tile, mbs in ((64, (None, 16, 18, 20)), (128, (None, 8, 9, 10)),
+                      (256, (None, 4, 5))):
+        for mb in mbs:
+            VARIANTS.append(dict(tile=tile, pass_budget=6, min_blocks=mb))
+SINGLE = [int(v) for v in os.environ.get('SWEEP_SINGLE_BUF', '1,0').split(',')]
 WAVES = [int(w) for w in os.environ.get('SWEEP_WAVES', '4,8').split(',')]
 
 
@@ -59,8 +66,9 @@ def run():
     import bench
     balg = bench.algorithmic_bytes_per_sample(nx, nu, ny)
     out = []
-    for v, waves in itertools.product(VARIANTS, WAVES):
+    for v, waves, single in itertools.product(VARIANTS, WAVES, SINGLE):
         os.environ['CFEM_WAVES'] = str(waves)
+        os.environ['CFEM_SINGLE_BUF'] = str(single)
         lib = backend.Library.load(backend.build_library(
             st, backend.structure_label(st), masks=(31,), **v))
         h = backend.Handle(lib, st.N, [d['source'] for d in st.data],
@@ -76,7 +84,7 @@ def run():
             h.eval(31)
             ms.append(h.last_sample_kernel_ms())
         ms = ms[3:]
-        rec = dict(v, waves=waves, ms_min=min(ms), ms_med=float(np.median(ms)),
+        rec = dict(v, waves=waves, single_buf=single, ms_min=min(ms), ms_med=float(np.median(ms)),
                    gbs=balg * N / (np.median(ms) * 1e-3) / 1e9)
         print(json.dumps(rec), flush=True)
         out.append(rec)
