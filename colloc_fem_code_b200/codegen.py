@@ -659,7 +659,9 @@ class Generator:
         for di, slot in enumerate(self.dyn_slots):
             w.append(f'    tot[{slot}] = cfem::reduce_tiles<CFEM_TILE>(part, '
                      f'a.ngroups, {nd}, {di}, scratch, tid);')
-        w.append('    if (tid != 0) return;')
+        w.append('    if (tid >= 32) return;      // warp 0 goes on; '
+                 'the sums are in thread 0')
+        w.append('    if (tid == 0) {')
         for fi, f in enumerate(self.funs):
             if not f['is_objective']:
                 continue
@@ -691,23 +693,30 @@ class Generator:
             w += undefs
         w.append(f'    for (int r = 0; r < {R}; ++r) '
                  f'a.reduce[b * {R} + r] = tot[r];')
+        w.append('    }')
         w.append('    // time-sharded run: exchange the partial sums with the peer '
-                 'GPUs through NVLink-mapped memory, inside this kernel')
+                 'GPUs through NVLink-mapped')
+        w.append('    // memory, inside this kernel; lane p of this warp talks '
+                 'to rank p')
         w.append('    if (a.peer_world > 1) {')
+        w.append(f'        for (int r = 0; r < {R}; ++r) '
+                 'tot[r] = __shfl_sync(0xffffffffu, tot[r], 0);')
         w.append('        if (a.peer_defer) {')
         w.append('            // pipelined mode: finish the PREVIOUS launch, post this one')
         w.append('            if (a.peer_epoch > 1ull && a.peer_prev_mask) {')
         w.append(f'                double prev[{R}];')
         w.append(f'                cfem::peer_collect<{R}>(a, b, (long long)gridDim.y, '
-                 'a.peer_epoch - 1ull, prev);')
-        w.append('                cfem_write_sums(a, a.peer_prev_mask, b, prev);')
+                 'a.peer_epoch - 1ull, prev, tid);')
+        w.append('                if (tid == 0) cfem_write_sums(a, a.peer_prev_mask, '
+                 'b, prev);')
         w.append('            }')
-        w.append(f'            cfem::peer_post<{R}>(a, b, tot);')
+        w.append(f'            cfem::peer_post<{R}>(a, b, (long long)gridDim.y, '
+                 'tot, tid);')
         w.append('            return;')
         w.append('        }')
-        w.append(f'        cfem::peer_allreduce<{R}>(a, b, tot);')
+        w.append(f'        cfem::peer_allreduce<{R}>(a, b, tot, tid);')
         w.append('    }')
-        w.append('    cfem_write_sums(a, mask, b, tot);')
+        w.append('    if (tid == 0) cfem_write_sums(a, mask, b, tot);')
         w.append('}')
         w.append('')
         w.append('__global__ void cfem_apply_reduced_kernel(const cfem::KArgs a, '
@@ -729,11 +738,10 @@ class Generator:
                  'const unsigned mask)')
         w.append('{')
         w.append('    const long long b = blockIdx.x;')
-        w.append('    if (threadIdx.x != 0) return;')
         w.append(f'    double tot[{R}];')
         w.append(f'    cfem::peer_collect<{R}>(a, b, (long long)gridDim.x, '
-                 'a.peer_epoch, tot);')
-        w.append('    cfem_write_sums(a, mask, b, tot);')
+                 'a.peer_epoch, tot, (int)threadIdx.x);')
+        w.append('    if (threadIdx.x == 0) cfem_write_sums(a, mask, b, tot);')
         w.append('}')
         return '\n'.join(w)
 

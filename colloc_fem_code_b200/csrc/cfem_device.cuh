@@ -362,8 +362,9 @@ __device__ __forceinline__ bool tree_reduce(const KArgs& a, long long b,
 // the CTA that finalises the rank's own sums (`tot`, R doubles per problem):
 //   1. store `tot` into slot [epoch % kPeerRing][my rank] of EVERY rank's inbox
 //      (peer stores through NVLink / NVSwitch-mapped memory);
-//   2. system-scope release store of the launch epoch into the matching flag;
-//   3. spin (acquire loads) until all `world` flags of the own inbox carry the
+//   2. one system-scope fence, then the launch epoch into the matching flag
+//      of every rank (relaxed system-scope stores);
+//   3. spin (relaxed loads, then one fence) until all `world` flags of the own inbox carry the
 //      epoch, then sum the inbox rows IN RANK ORDER -- every rank computes the
 //      same bits -- and continue with the global sums.
 // No NCCL launch, no host round trip: the collective costs two NVLink
@@ -391,14 +392,19 @@ __device__ __forceinline__ bool tree_reduce(const KArgs& a, long long b,
 constexpr int kPeerRing = 4;
 constexpr unsigned long long kPeerSpinNs = 20ull * 1000ull * 1000ull * 1000ull;
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+// System-scope relaxed accesses for the flags.  Ordering comes from ONE
+// __threadfence_system() per hand-shake side (fence; relaxed store = release,
+// relaxed load; fence = acquire) instead of a release/acquire per flag: with W
+// peers a st.release.sys per flag is W back-to-back system fences, each
+// waiting for the previous remote store to be acknowledged over NVLink.
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v)
 {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p)
 {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long global_ns()
@@ -408,63 +414,80 @@ __device__ __forceinline__ unsigned long long global_ns()
     return t;
 }
 
+// The hand-shake is executed by ONE WARP (all 32 lanes call these functions
+// with the same arguments); lane p talks to rank p, so the W remote stores,
+// the W flag polls and the W row loads are in flight together: the exchange
+// costs about two NVLink latencies whatever the number of ranks.
+
 // Wait until the flags of `epoch` from all ranks are in the own inbox.
-__device__ __forceinline__ bool peer_wait(const KArgs& a, unsigned long long epoch)
+__device__ __forceinline__ bool peer_wait(const KArgs& a, unsigned long long epoch, int lane)
 {
     const int W = a.peer_world;
-    const unsigned long long* myflag =
-        a.peer_flag[a.peer_rank] + (long long)(epoch % kPeerRing) * W;
-    const unsigned long long t0 = global_ns();
-    for (int p = 0; p < W; ++p) {
-        while (ld_acquire_sys(myflag + p) < epoch) {
-            __nanosleep(64);
-            if (global_ns() - t0 > kPeerSpinNs) return false;
+    bool ok = true;
+    if (lane < W) {
+        const unsigned long long* myflag =
+            a.peer_flag[a.peer_rank] + (long long)(epoch % kPeerRing) * W + lane;
+        const unsigned long long t0 = global_ns();
+        while (ld_relaxed_sys(myflag) < epoch) {
+            __nanosleep(32);
+            if (global_ns() - t0 > kPeerSpinNs) { ok = false; break; }
         }
+        __threadfence_system();     // acquire: rank `lane`'s sums are visible now
     }
-    return true;
+    return __all_sync(0xffffffffu, ok);
 }
 
 template <int R>
-__device__ __forceinline__ void peer_post(const KArgs& a, long long b, const double (&tot)[R])
+__device__ __forceinline__ void peer_post(const KArgs& a, long long b, long long nb,
+                                          const double (&tot)[R], int lane)
 {
     const int W = a.peer_world, me = a.peer_rank;
     const unsigned long long epoch = a.peer_epoch;
     const long long slot = (long long)(epoch % kPeerRing);
-    const long long nb = (long long)gridDim.y;              // problems per launch
-    const long long row = (slot * W + me) * nb * R + b * R;
-    for (int p = 0; p < W; ++p) {
-        double* dst = a.peer_inbox[p] + row;
+    if (lane < W) {
+        double* dst = a.peer_inbox[lane] + (slot * W + me) * nb * R + b * R;
 #pragma unroll
         for (int r = 0; r < R; ++r) __stcg(dst + r, tot[r]);
+        __threadfence_system();     // release: the sums before the flag
+        // one flag per (slot, rank, problem) would be needed for batches; a
+        // time-sharded problem has batch == 1, enforced on the host
+        st_relaxed_sys(a.peer_flag[lane] + slot * W + me, epoch);
     }
-    __threadfence_system();
-    // one flag per (slot, rank, problem) would be needed for batches; a
-    // time-sharded problem has batch == 1, enforced on the host
-    for (int p = 0; p < W; ++p) st_release_sys(a.peer_flag[p] + slot * W + me, epoch);
+    __syncwarp();
 }
 
-// Rank-order sum of the inbox rows of `epoch` (after all flags arrived).
+// Rank-order sum of the inbox rows of `epoch` (after all flags arrived):
+// identical bits on every rank, in every lane.
 template <int R>
 __device__ __forceinline__ void peer_collect(const KArgs& a, long long b, long long nb,
-                                             unsigned long long epoch, double (&tot)[R])
+                                             unsigned long long epoch, double (&tot)[R],
+                                             int lane)
 {
     const int W = a.peer_world;
-    const bool ok = peer_wait(a, epoch);
+    const bool ok = peer_wait(a, epoch, lane);
     const long long slot = (long long)(epoch % kPeerRing);
-    const double* in = a.peer_inbox[a.peer_rank] + slot * W * nb * R + b * R;
+    double mine[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) mine[r] = 0.0;
+    if (lane < W) {
+        const double* in = a.peer_inbox[a.peer_rank] + (slot * W + lane) * nb * R + b * R;
+#pragma unroll
+        for (int r = 0; r < R; ++r) mine[r] = __ldcv(in + r);
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) tot[r] = ok ? 0.0 : __longlong_as_double(0x7ff8000000000000ll);
     for (int p = 0; p < W; ++p) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) tot[r] += __ldcv(in + (long long)p * nb * R + r);
+        for (int r = 0; r < R; ++r) tot[r] += __shfl_sync(0xffffffffu, mine[r], p);
     }
 }
 
 template <int R>
-__device__ __forceinline__ void peer_allreduce(const KArgs& a, long long b, double (&tot)[R])
+__device__ __forceinline__ void peer_allreduce(const KArgs& a, long long b, double (&tot)[R],
+                                               int lane)
 {
-    peer_post<R>(a, b, tot);
-    peer_collect<R>(a, b, (long long)gridDim.y, a.peer_epoch, tot);
+    peer_post<R>(a, b, (long long)gridDim.y, tot, lane);
+    peer_collect<R>(a, b, (long long)gridDim.y, a.peer_epoch, tot, lane);
 }
 
 }  // namespace cfem

@@ -244,6 +244,7 @@ class ShardedEvaluator:
         buf.zero_()
         hdl = symm.rendezvous(buf, group)
         ptrs = [int(p) for p in hdl.buffer_ptrs]
+        ptrs[rank] = buf.data_ptr()     # own inbox: the local mapping
         torch.cuda.synchronize()
         dist.barrier(group)             # every inbox is zeroed before any store
         self.handle.set_peers(rank, world, ptrs,

@@ -1,4 +1,10 @@
 set -x
-SWEEP_WAVES=8,16 timeout 900 python tools/sweep.py run > gpurun_out/sweep6_212.log 2> gpurun_out/sweep6_212.err; tail -n 3 gpurun_out/sweep6_212.err; cat gpurun_out/sweep6_212.log
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -n 3
-timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/b1_r1n.json 2> gpurun_out/b1_r1n.err; echo "bench1 rc=$?"; cat gpurun_out/b1_r1n.json
+for n in 8; do
+for mode in peer nccl; do
+CFEM_REDUCE=$mode timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 30 --warmup 5 > gpurun_out/scale_${n}_$mode.json 2> gpurun_out/scale_${n}_$mode.err; echo "bench $n rc=$?"
+python -c "
+import json; d=json.load(open('gpurun_out/scale_${n}_$mode.json')); print(d['value'], d['ms_per_step'], d['per_rank'], d['e2e']['value'], d['wall_s_timed_region'], d['host_enqueue_s'])"
+done
+done
+CUDA_VISIBLE_DEVICES=3 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/scale_1_samebox.json 2>/dev/null; python -c "
+import json; d=json.load(open('gpurun_out/scale_1_samebox.json')); print(d['value'], d['ms_per_step'], d['per_rank'])"
