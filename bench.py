@@ -130,16 +130,19 @@ class ClockSampler:
 
 def bind_to_gpu_numa_node(device):
     """Pin this process to the CPUs of the GPU's NUMA node so that the pinned
-    host buffers (first touch) and the DMA engines sit on the same socket."""
+    host buffers (first touch) and the DMA engines sit on the same socket.
+    Returns (node or None, note)."""
     try:
-        import torch
-        props = torch.cuda.get_device_properties(device)
-        bus = f'{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:' \
-              f'{props.pci_device_id:02x}.0'
+        out = subprocess.run(
+            ['nvidia-smi', '-i', str(device), '--query-gpu=pci.bus_id',
+             '--format=csv,noheader'], capture_output=True, text=True,
+            timeout=30).stdout.strip().lower()
+        dom, rest = out.split(':', 1)
+        bus = f'{dom[-4:]}:{rest}'
         with open(f'/sys/bus/pci/devices/{bus}/numa_node') as fh:
             node = int(fh.read())
         if node < 0:
-            return None
+            return None, f'{bus}: numa_node {node} (no NUMA information)'
         with open(f'/sys/devices/system/node/node{node}/cpulist') as fh:
             cpus = set()
             for part in fh.read().strip().split(','):
@@ -148,9 +151,9 @@ def bind_to_gpu_numa_node(device):
         allowed = os.sched_getaffinity(0) & cpus
         if allowed:
             os.sched_setaffinity(0, allowed)
-        return node
-    except Exception:
-        return None
+        return node, f'{bus}: bound to {len(allowed)} CPUs of node {node}'
+    except Exception as exc:
+        return None, repr(exc)
 
 
 class CudaArray:
@@ -214,10 +217,11 @@ def workload_config(world, reduce_mode='none'):
     nx, nu, ny = DIMS
     how = {'skip': 'NO reduction (debug only: results incomplete)',
            'peer': 'objective + parameter gradient: partial sums posted to '
-                   'every peer inside the kernel over NVLink peer memory, '
-                   'rank-order sum by a collect kernel on a side stream that '
-                   'overlaps the next step (every step is collected inside '
-                   'the timed region; no NCCL call on the path)',
+                   'every peer inside the kernel over NVLink peer memory; '
+                   'the rank-order sum of step k is finished inside the '
+                   'kernel of step k+1 (by a collect kernel after the last '
+                   'step), so ranks do not rendezvous at every step; no '
+                   'NCCL call on the path',
            'peer_sync': 'objective + parameter gradient reduced inside the '
                         'kernel over NVLink peer memory, all ranks rendezvous '
                         'at the end of every kernel (no NCCL call on the '
@@ -276,7 +280,7 @@ def run_ours(args, out):
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
     torch.cuda.set_device(local_rank)
-    numa_node = bind_to_gpu_numa_node(local_rank)
+    numa_node, numa_note = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device(
@@ -503,7 +507,7 @@ def run_ours(args, out):
             'data': 'synthetic',
             'config': workload_config(world, reduce_mode),
             'samples_per_s': value * N_PER_GPU,
-            'numa_node': numa_node,
+            'numa_node': numa_node, 'numa_note': numa_note,
             'per_rank': per_rank,
             'ms_per_step_with_kernel_events': sum(probe['step_ms'])
             / args.steps,

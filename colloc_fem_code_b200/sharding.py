@@ -313,20 +313,24 @@ class SharedVectors:
         self._registered = None
 
     def _create(self, total):
-        """Backing store: a tmpfs file under /dev/shm whose pages are reserved
-        up front (``posix_fallocate`` -- a too-small /dev/shm fails here with
-        ENOSPC, not later with SIGBUS); else an anonymous memfd that the other
-        ranks open through ``/proc/<pid>/fd``."""
+        """Backing store: a tmpfs file under /dev/shm if it has room (checked
+        up front -- a too-small /dev/shm would fail later with SIGBUS); else an
+        anonymous memfd that the other ranks open through ``/proc/<pid>/fd``.
+        Pages are NOT allocated here: every rank first-touches its own pieces
+        (``SolverFacingEvaluator``), which places them on the NUMA node of the
+        rank that will DMA them."""
         import uuid
         path = f'/dev/shm/cfem_{os.getpid()}_{uuid.uuid4().hex[:12]}'
         try:
-            fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
-            try:
-                os.posix_fallocate(fd, 0, total)
-                return path, fd
-            except OSError:
-                os.close(fd)
-                os.unlink(path)
+            vfs = os.statvfs('/dev/shm')
+            if vfs.f_bavail * vfs.f_frsize > total + (64 << 20):
+                fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                try:
+                    os.ftruncate(fd, total)
+                    return path, fd
+                except OSError:
+                    os.close(fd)
+                    os.unlink(path)
         except OSError:
             pass
         fd = os.memfd_create('cfem_shared_vectors')
@@ -409,7 +413,6 @@ class SolverFacingEvaluator:
                 broadcast([None])       # the other ranks must not hang
                 raise
             self.sv.ctrl[:] = 0
-            self.sv.lam[:] = 0.0
             broadcast([self.sv.path])
         else:
             box = [None]
@@ -420,10 +423,20 @@ class SolverFacingEvaluator:
             self.sv = SharedVectors(sizes, world, path=box[0])
         barrier()                       # everybody has mapped the segment
         self.sv.unlink()
-        self.pinned = self.sv.page_lock(lib) if lib is not None else False
         self._in = {k: shard.input_pieces(k) for k in ('dvec', 'lam')}
         self._out = {k: shard.result_pieces(k)
                      for _, k in self.RESULTS}
+        # first touch: the pages of a rank's pieces are allocated by that rank
+        # (its NUMA node, if the process is bound to the GPU's node) before
+        # they are page-locked; fresh shared-memory pages are zero-filled
+        for name, pieces in list(self._out.items()) + list(self._in.items()):
+            vec = getattr(self.sv, name)
+            for _, g0, n in pieces:
+                if name in ('dvec', 'lam') and n < 4096:
+                    continue            # replicated parameters: whoever is first
+                vec[g0:g0 + n] = 0.0
+        barrier()
+        self.pinned = self.sv.page_lock(lib) if lib is not None else False
         self._seq = 0
         self._have_x = False
         self._fresh = 0

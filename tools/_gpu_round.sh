@@ -1,10 +1,12 @@
 set -x
-for n in 8; do
-for mode in peer nccl; do
-CFEM_REDUCE=$mode timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 30 --warmup 5 > gpurun_out/scale_${n}_$mode.json 2> gpurun_out/scale_${n}_$mode.err; echo "bench $n rc=$?"
-python -c "
-import json; d=json.load(open('gpurun_out/scale_${n}_$mode.json')); print(d['value'], d['ms_per_step'], d['per_rank'], d['e2e']['value'], d['wall_s_timed_region'], d['host_enqueue_s'])"
-done
-done
-CUDA_VISIBLE_DEVICES=3 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/scale_1_samebox.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/scale_1_samebox.json')); print(d['value'], d['ms_per_step'], d['per_rank'])"
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_final.log 2>&1; echo "pytest rc=$?"
+tail -n 3 gpurun_out/pytest_gpu_final.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -n 2 gpurun_out/smoke.log
+timeout 900 python tools/roofline_table.py > gpurun_out/roofline_table.jsonl 2> gpurun_out/roofline_table.err; echo "table rc=$?"; cat gpurun_out/roofline_table.jsonl
+timeout 600 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_r1q.csv python bench.py --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/ncu1.log 2>&1
+echo "ncu1 rc=$?"
+timeout 600 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:cfem_sample_kernel_m31 -s 4 -c 2 -f -o gpurun_out/prof_r1q python bench.py --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/ncu2.log 2>&1
+echo "ncu2 rc=$?"
+cat gpurun_out/plain.log | tail -n 2
