@@ -534,8 +534,10 @@ class Generator:
         return '\n'.join(w), lay['total'] * 8
 
     def _param_entries(self):
-        """(kind bit, dest expr, value code, fun) for every entry of the
-        parameter-only functions; grouped G, JAC, HESS."""
+        """Every entry of the parameter-only functions, grouped G, JAC, HESS:
+        dicts with the function, its dependencies, the destination (array
+        kind, block, offset), the value code and the multiplier of Hessian
+        entries (a constraint multiplier or obj_factor)."""
         st = self.st
         ents = {G: [], JAC: [], HESS: []}
         for fi in self.param_funs:
@@ -545,42 +547,154 @@ class Generator:
                 continue
             ci = f['cons_index']
             for e in spec.values:
-                ents[G].append((f, e.deps, f'a.g[b * a.ncons + '
-                                f'a.cons_off[{ci}] + {e.index[0]}]', e.code))
+                ents[G].append(dict(fun=f, deps=e.deps, kind=0, blk=ci,
+                                    off=e.index[0], code=e.code, mult=None))
         for bi, blk in enumerate(st.jac_blocks):
             f = self.funs[blk['fun']]
             if f['per_sample']:
                 continue
             for j, e in enumerate(blk['entries']):
-                ents[JAC].append((f, e.deps, f'a.jac[b * a.nnz_jac + '
-                                  f'a.jac_off[{bi}] + {j}]', e.code))
+                ents[JAC].append(dict(fun=f, deps=e.deps, kind=1, blk=bi,
+                                      off=j, code=e.code, mult=None))
         for bi, blk in enumerate(st.hess_blocks):
             f = self.funs[blk['fun']]
             if f['per_sample']:
                 continue
             for j, e in enumerate(blk['entries']):
-                if f['is_objective']:
-                    mult = 'a.obj_factor'
-                else:
-                    mult = (f'lam[a.cons_off[{f["cons_index"]}] + '
-                            f'{e.index[2]}]')
-                ents[HESS].append((f, e.deps, f'a.hess[b * a.nnz_hess + '
-                                   f'a.hess_off[{bi}] + {j}]',
-                                   f'({mult}) * ({e.code})'))
+                mult = (('sigma',) if f['is_objective'] else
+                        ('lam', f['cons_index'], e.index[2]))
+                ents[HESS].append(dict(fun=f, deps=e.deps, kind=2, blk=bi,
+                                       off=j, code=e.code, mult=mult))
         return ents
+
+    _DEST = ('a.g[b * a.ncons + a.cons_off[{blk}] + {off}]',
+             'a.jac[b * a.nnz_jac + a.jac_off[{blk}] + {off}]',
+             'a.hess[b * a.nnz_hess + a.hess_off[{blk}] + {off}]')
+
+    @staticmethod
+    def _mult_code(mult):
+        if mult is None:
+            return None
+        if mult[0] == 'sigma':
+            return 'a.obj_factor'
+        return f'lam[a.cons_off[{mult[1]}] + {mult[2]}]'
+
+    @staticmethod
+    def _parse_flat(code):
+        """``code`` as a flat sum of products ``[(coeff, [identifier, ...])]``
+        in the printed order, or None if it is anything else (parentheses,
+        divisions, function calls).  ``a - b*c`` becomes ``+1*a`` and
+        ``-1*b*c``: sign flips are exact in IEEE arithmetic, so evaluating the
+        terms left to right reproduces the printed expression."""
+        import re
+        if re.search(r'[()/]', code):
+            return None
+        toks = re.split(r'\s([+-])\s', code.strip())
+        terms, sign = [], 1.0
+        first = toks[0].strip()
+        if first.startswith('-'):
+            sign, first = -1.0, first[1:].strip()
+        toks[0] = first
+        i = 0
+        while i < len(toks):
+            body = toks[i]
+            facs = [t.strip() for t in body.split('*')]
+            coeff, idents = 1.0, []
+            for k, t in enumerate(facs):
+                if re.fullmatch(r'v_[A-Za-z0-9_]+', t):
+                    idents.append(t)
+                elif k == 0 and re.fullmatch(
+                        r'[0-9]+(\.[0-9]*)?([eE][-+]?[0-9]+)?', t):
+                    coeff = float(t)
+                else:
+                    return None
+            terms.append((sign * coeff, idents))
+            if i + 1 < len(toks):
+                sign = 1.0 if toks[i + 1] == '+' else -1.0
+            i += 2
+        return terms
 
     #: entries per __noinline__ chunk function of the parameter kernel (ptxas
     #: time grows super-linearly with the size of one function)
     PARAM_CHUNK = 32
 
+    def _pack_factor(self, fun, arg, flat):
+        """Operand of a table term: space (0 decision variable, 1 scalar),
+        index of the variable / scalar, element."""
+        ref = fun['args'][arg]
+        space = {'param': 0, 'scalar': 1}[ref[0]]
+        assert 0 <= ref[1] < 1024 and 0 <= flat < (1 << 20)
+        return (space << 30) | (ref[1] << 20) | (flat if space == 0 else 0)
+
     def _emit_param_kernel(self):
+        """The parameter-only constraints are polynomials of the parameters.
+        Entries that print as a flat sum of products (over 90 % of them) go
+        into a TABLE -- per entry a destination, a term range and an optional
+        multiplier (lambda / obj_factor); per term a coefficient and a factor
+        range -- evaluated by one uniform loop, a thread per (entry, problem):
+        no per-entry code, no divergence, compile time and instruction-cache
+        footprint independent of the number of entries.  The rest (nested,
+        Horner-like expressions of the ZOH discretisation) keeps generated
+        straight-line code, one WARP per entry."""
         ents = self._param_entries()
         order = ents[G] + ents[JAC] + ents[HESS]
-        n_g, n_j = len(ents[G]), len(ents[JAC])
         self.n_param_entries = len(order)
+        table, code_ents = [], []
+        for ent in order:
+            terms = self._parse_flat(ent['code'])
+            if terms is None:
+                code_ents.append(ent)
+                continue
+            idmap = {symoptim.c_ident(a_, fl): (a_, fl) for a_, fl in ent['deps']}
+            if any(i not in idmap for _, ids in terms for i in ids):
+                code_ents.append(ent)
+                continue
+            ent['terms'] = [(c, [self._pack_factor(ent['fun'], *idmap[i])
+                                 for i in ids]) for c, ids in terms]
+            table.append(ent)
+        self.n_param_table, self.n_param_code = len(table), len(code_ents)
         CH = self.PARAM_CHUNK
         w = []
-        nchunks = (len(order) + CH - 1) // CH
+        # ---- tables
+        term0, coeffs, fac0, facs, dests, mults = [0], [], [0], [], [], []
+        for ent in table:
+            for c, fl in ent['terms']:
+                coeffs.append(c)
+                facs += fl
+                fac0.append(len(facs))
+            term0.append(len(coeffs))
+            assert ent['blk'] < 1024 and ent['off'] < (1 << 20)
+            dests.append((ent['kind'] << 30) | (ent['blk'] << 20) | ent['off'])
+            m = ent['mult']
+            if m is None:
+                mults.append(0xFFFFFFFF)
+            elif m[0] == 'sigma':
+                mults.append(0xFFFFFFFE)
+            else:
+                assert m[1] < 1024 and m[2] < (1 << 20)
+                mults.append((m[1] << 20) | m[2])
+
+        def arr(ctype, name, vals, fmt):
+            body = ', '.join(fmt(v) for v in vals) if vals else fmt(0)
+            lines = [f'static __device__ const {ctype} {name}'
+                     f'[{max(1, len(vals))}] = {{']
+            items = body.split(', ')
+            for i in range(0, len(items), 12):
+                lines.append('    ' + ', '.join(items[i:i + 12]) + ',')
+            lines.append('};')
+            return lines
+        w.append(f'constexpr int kParamTable = {len(table)};   '
+                 '// entries evaluated from the tables')
+        w.append(f'constexpr int kParamCode = {len(code_ents)};    '
+                 '// entries with generated code')
+        w += arr('int', 'kPE_term0', term0, str)
+        w += arr('unsigned', 'kPE_dest', dests, lambda v: f'{v}u')
+        w += arr('unsigned', 'kPE_mult', mults, lambda v: f'{v}u')
+        w += arr('double', 'kPT_coeff', coeffs, lambda v: repr(float(v)))
+        w += arr('int', 'kPT_fac0', fac0, str)
+        w += arr('unsigned', 'kPF', facs, lambda v: f'{v}u')
+        # ---- generated code for the remaining entries
+        nchunks = (len(code_ents) + CH - 1) // CH
         for c in range(nchunks):
             w.append(f'static __device__ __noinline__ void cfem_param_chunk{c}('
                      'const cfem::KArgs& a, const long long b, const int e)')
@@ -589,19 +703,30 @@ class Generator:
             w.append('    const double* __restrict__ lam = a.lam + b * a.ncons;')
             w.append('    (void)dvec; (void)lam;')
             w.append('    switch (e) {')
-            for i in range(c * CH, min(len(order), (c + 1) * CH)):
-                f, deps, dest, code = order[i]
+            for i in range(c * CH, min(len(code_ents), (c + 1) * CH)):
+                ent = code_ents[i]
+                dest = self._DEST[ent['kind']].format(**ent)
+                mult = self._mult_code(ent['mult'])
+                code = ent['code'] if mult is None else \
+                    f'({mult}) * ({ent["code"]})'
                 w.append(f'    case {i}: {{')
-                defs, undefs = self._define_args(f, deps, 'global')
+                defs, undefs = self._define_args(ent['fun'], ent['deps'],
+                                                 'global')
                 w += defs
-                w.append(f'        {dest} = {code};')
+                w.append(f'        if (mask & {(G, JAC, HESS)[ent["kind"]]}u) '
+                         f'{dest} = {code};')
                 w += undefs
                 w.append('        break; }')
             w.append('    default: break;')
             w.append('    }')
             w.append('}')
-        w.append('// Entry `e` of the parameter-only constraints (value, Jacobian '
-                 'or Hessian entry).')
+        for c in range(nchunks):    # the chunks take the mask
+            pass
+        text = '\n'.join(w).replace(
+            'const cfem::KArgs& a, const long long b, const int e)',
+            'const cfem::KArgs& a, const unsigned mask, const long long b, '
+            'const int e)')
+        w = [text]
         w.append('// Launched right before the per-sample kernel on the same '
                  'stream; the latter is')
         w.append('// launched with programmatic stream serialisation and never '
@@ -610,21 +735,54 @@ class Generator:
                  'a second stream or')
         w.append('// fork/join events: this kernel releases its dependents '
                  'first thing.')
-        w.append('__global__ void __launch_bounds__(64)')
+        w.append(f'constexpr int kParamTableCtas = ({len(table)} + 127) / 128;')
+        w.append('__global__ void __launch_bounds__(128)')
         w.append('cfem_param_kernel(const __grid_constant__ cfem::KArgs a, '
-                 'const unsigned mask)')
+                 'const unsigned mask, const int batch)')
         w.append('{')
         w.append('    asm volatile("griddepcontrol.launch_dependents;");')
-        w.append('    const int e = blockIdx.x * 64 + threadIdx.x;')
-        w.append('    const long long b = blockIdx.y;')
-        w.append(f'    if (e >= {len(order)}) return;')
-        w.append(f'    if (e < {n_g}) {{ if (!(mask & {G}u)) return; }}')
-        w.append(f'    else if (e < {n_g + n_j}) '
-                 f'{{ if (!(mask & {JAC}u)) return; }}')
-        w.append(f'    else {{ if (!(mask & {HESS}u)) return; }}')
+        w.append('    const long long b = blockIdx.y;      // problem of a batch')
+        w.append('    (void)batch;')
+        w.append('    if ((int)blockIdx.x < kParamTableCtas) {')
+        w.append('        // table entries: a thread per entry, one uniform loop')
+        w.append('        const int e = blockIdx.x * 128 + threadIdx.x;')
+        w.append('        if (e >= kParamTable) return;')
+        w.append('        const unsigned dest = kPE_dest[e];')
+        w.append('        const unsigned kind = dest >> 30;')
+        w.append(f'        if (!(mask & ({G}u << kind))) return;')
+        w.append('        const double* __restrict__ dvec = a.dvec + b * a.ndec;')
+        w.append('        double sum = 0.0;')
+        w.append('        for (int t = kPE_term0[e]; t < kPE_term0[e + 1]; ++t) {')
+        w.append('            double p = kPT_coeff[t];')
+        w.append('            for (int k = kPT_fac0[t]; k < kPT_fac0[t + 1]; ++k) {')
+        w.append('                const unsigned f = kPF[k];')
+        w.append('                const double v = (f >> 30) == 0u ? '
+                 'dvec[a.var_off[(f >> 20) & 1023u] + (f & 0xFFFFFu)] '
+                 ': a.scalars[(f >> 20) & 1023u];')
+        w.append('                p = __dmul_rn(p, v);     // printed order, no contraction')
+        w.append('            }')
+        w.append('            sum = __dadd_rn(sum, p);')
+        w.append('        }')
+        w.append('        const unsigned m = kPE_mult[e];')
+        w.append('        if (m == 0xFFFFFFFEu) sum = __dmul_rn(a.obj_factor, sum);')
+        w.append('        else if (m != 0xFFFFFFFFu) sum = __dmul_rn('
+                 'a.lam[b * a.ncons + a.cons_off[m >> 20] + (m & 0xFFFFFu)], sum);')
+        w.append('        const long long blk = (dest >> 20) & 1023u, '
+                 'off = dest & 0xFFFFFu;')
+        w.append('        if (kind == 0u) a.g[b * a.ncons + a.cons_off[blk] + off] = sum;')
+        w.append('        else if (kind == 1u) a.jac[b * a.nnz_jac + a.jac_off[blk] + off] = sum;')
+        w.append('        else a.hess[b * a.nnz_hess + a.hess_off[blk] + off] = sum;')
+        w.append('        return;')
+        w.append('    }')
+        w.append('    // generated entries: each has its own straight-line code, '
+                 'ONE WARP per entry')
+        w.append('    // (a thread per entry would make every warp 32-way divergent)')
+        w.append('    const int e = ((int)blockIdx.x - kParamTableCtas) * 4 + '
+                 '(threadIdx.x >> 5);')
+        w.append('    if (e >= kParamCode || (threadIdx.x & 31)) return;')
         w.append(f'    switch (e / {CH}) {{')
         for c in range(nchunks):
-            w.append(f'    case {c}: cfem_param_chunk{c}(a, b, e); break;')
+            w.append(f'    case {c}: cfem_param_chunk{c}(a, mask, b, e); break;')
         w.append('    default: break;')
         w.append('    }')
         w.append('}')
@@ -845,9 +1003,9 @@ class Generator:
         w.append(launch_param_sig)
         w.append('{')
         if self.n_param_entries:
-            w.append(f'    const dim3 grid(({self.n_param_entries} + 63) / 64, '
+            w.append('    const dim3 grid(kParamTableCtas + (kParamCode + 3) / 4, '
                      'batch);')
-            w.append('    cfem_param_kernel<<<grid, 64, 0, s>>>(a, mask);')
+            w.append('    cfem_param_kernel<<<grid, 128, 0, s>>>(a, mask, batch);')
             w.append('    return cudaGetLastError();')
         else:
             w.append('    (void)mask; (void)batch; (void)s; (void)a;')

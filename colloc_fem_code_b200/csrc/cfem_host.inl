@@ -42,7 +42,7 @@ struct cfem_problem {
     };
     StepGraph     graphs[gen::kNumMasks];
     bool          use_graph = false;            // cfem_set_graph_mode / CFEM_GRAPH
-    bool          use_pdl = true;               // overlap the two kernels by programmatic dependent launch (CFEM_PDL)
+    int           use_pdl = 1;                  // CFEM_PDL: 0 fork/join, 1 programmatic dependent launch for long kernels, 2 always
     bool          skip_param = false;           // CFEM_SKIP_PARAM: step-overhead experiments only (results incomplete)
     long long     N = 0;
     int           batch = 1;
@@ -247,7 +247,7 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     p->sm_count = sm_count;
     if (const char* w = getenv("CFEM_WAVES")) { p->waves = atoi(w) > 0 ? atoi(w) : 1; }
     if (const char* w = getenv("CFEM_PREFETCH")) { p->prefetch = atoll(w); }
-    if (const char* w = getenv("CFEM_PDL")) { p->use_pdl = atoi(w) != 0; }
+    if (const char* w = getenv("CFEM_PDL")) { p->use_pdl = atoi(w); }
     if (const char* w = getenv("CFEM_GRAPH")) { p->use_graph = atoi(w) != 0; }
     if (const char* w = getenv("CFEM_SKIP_PARAM")) { p->skip_param = atoi(w) != 0; }   // measurement only
     p->N = n_samples;
@@ -485,7 +485,8 @@ static int cfem_launch_graph(cfem_problem* p, unsigned mask, bool params)
         if (params && memcmp(&g.a2, &p->k, sizeof(cfem::KArgs)) != 0) {
             g.a2 = p->k;
             unsigned m = mask;
-            void* args[2] = {&g.a2, &m};
+            int nb = p->batch;
+            void* args[3] = {&g.a2, &m, &nb};
             cudaKernelNodeParams kp = g.p2;
             kp.kernelParams = args;
             kp.extra = nullptr;
@@ -517,11 +518,16 @@ int cfem_eval(cfem_problem* p, uint32_t what)
         // one graph launch: both kernels as parallel nodes, no stream events
         int rc = cfem_launch_graph(p, mask, params);
         if (rc) return rc;
-    } else if (params && p->use_pdl && !p->timing) {
+    } else if (params && !p->timing &&
+               (p->use_pdl >= 2 ||
+                (p->use_pdl == 1 && p->k.ntiles * p->batch > 4ll * p->sm_count))) {
         // Both kernels on ONE stream, no events: the parameter-only kernel
         // releases its dependents at once (griddepcontrol.launch_dependents),
         // the per-sample kernel is launched with programmatic stream
-        // serialisation and never waits on it -- they overlap.
+        // serialisation and never waits on it -- they overlap.  Used when the
+        // per-sample kernel is long (fewer driver calls per evaluation); at
+        // the native trajectory lengths, where one evaluation is 15-40 us, the
+        // two launches start about 1 us earlier from two streams (fork/join).
         CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->stream, p->k));
         CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, true, p->stream, p->k));
     } else {

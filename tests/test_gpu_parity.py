@@ -321,7 +321,7 @@ def test_launch_variants_give_identical_bits(kind, dims, N, batch, monkeypatch):
     dvec = np.stack([c[1] for c in cases])
     lam = np.stack([c[2] for c in cases])
     results = {}
-    for label, env in (('pdl', {}),
+    for label, env in (('pdl', {'CFEM_PDL': '2'}),
                        ('fork-join', {'CFEM_PDL': '0'}),
                        ('graph', {'CFEM_PDL': '0', 'CFEM_GRAPH': '1'})):
         for k in ('CFEM_PDL', 'CFEM_GRAPH'):

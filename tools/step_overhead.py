@@ -49,7 +49,8 @@ def main():
         dvec, lam, sigma = synthetic.evaluation_point(p, exp)
         lib = backend.Library.for_structure(st)
         for label, env, timing in (('default+timing', {}, True),
-                                   ('default (pdl)', {}, False),
+                                   ('default', {}, False),
+                                   ('pdl', {'CFEM_PDL': '2'}, False),
                                    ('fork-join', {'CFEM_PDL': '0'}, False),
                                    ('no param kernel', {'CFEM_SKIP_PARAM': '1'},
                                     False),
