@@ -431,8 +431,7 @@ def run_ours(args, out):
 
         def e2e_step(i):
             host.dvec[0] = ldvec[0] + 1e-12 * i      # a new x every step
-            h.set_dvec(host.dvec)
-            h.set_multipliers(sigma, host.lam)
+            host.upload(sigma)           # one H2D copy: [x | lambda]
             h.eval(backend.ALL)
             if reduce_mode == 'nccl':
                 dist.all_reduce(red)
@@ -456,9 +455,9 @@ def run_ours(args, out):
         e2e_ms = float(e2e_ms.item())
         e2e_h2d = int(8 * (h.ndec + h.ncons))
         e2e_d2h = int(8 * (1 + h.ndec + h.ncons + h.nnz_jac + h.nnz_hess))
-        e2e_note = ('pinned host dvec+lambda -> H2D -> fused kernels -> D2H of '
-                    'f, grad, g, Jacobian and Hessian values (per rank); '
-                    'CUDA events')
+        e2e_note = ('pinned host [dvec | lambda] -> one H2D copy -> fused '
+                    'kernels -> one D2H copy of [f | grad | g | Jacobian | '
+                    'Hessian values] (per rank); CUDA events')
     else:
         e2e_ms = 0.0
         if rank == 0:

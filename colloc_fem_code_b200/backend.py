@@ -72,6 +72,13 @@ ABI = {
                                   ctypes.c_void_p]),
     'cfem_fetch_async': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32,
                                         ctypes.c_void_p]),
+    'cfem_io_layout': (ctypes.c_int, [ctypes.c_void_p, _c_int64_p, _c_int64_p,
+                                      _c_int64_p, _c_int64_p]),
+    'cfem_set_inputs': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32,
+                                       ctypes.c_double, ctypes.c_void_p]),
+    'cfem_fetch_results_async': (ctypes.c_int, [ctypes.c_void_p,
+                                                ctypes.c_uint32,
+                                                ctypes.c_void_p]),
     'cfem_upload_pieces': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32,
                                           ctypes.c_void_p, ctypes.c_int32,
                                           ctypes.c_void_p, ctypes.c_void_p,
@@ -375,6 +382,24 @@ class Handle:
         self._check(self.lib.cfem_fetch_async(self._ptr, int(which),
                                               out.ctypes.data))
 
+    def io_layout(self):
+        """Segment offsets / totals (doubles) of the input and result slabs."""
+        ino = (ctypes.c_int64 * 2)()
+        reo = (ctypes.c_int64 * 5)()
+        it, rt = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self.lib.cfem_io_layout(
+            self._ptr, ino, ctypes.byref(it), reo, ctypes.byref(rt)))
+        return list(ino), it.value, list(reo), rt.value
+
+    def set_inputs(self, which, obj_factor, host_block):
+        self._check(self.lib.cfem_set_inputs(self._ptr, int(which),
+                                             float(obj_factor),
+                                             host_block.ctypes.data))
+
+    def fetch_results_async(self, which, host_block):
+        self._check(self.lib.cfem_fetch_results_async(
+            self._ptr, int(which), host_block.ctypes.data))
+
     @staticmethod
     def _piece_arrays(pieces):
         arr = np.ascontiguousarray(pieces, dtype=np.int64).reshape(-1, 3)
@@ -497,32 +522,50 @@ class PinnedArray:
 
 class HostBuffers:
     """Page-locked host staging for every input and result of a handle: the
-    buffers an NLP solver's callbacks read from / write to."""
+    buffers an NLP solver's callbacks read from / write to.  ONE block for the
+    inputs and ONE for the results, laid out like the device slabs
+    (``cfem_io_layout``), so that a callback set is one H2D and one D2H copy;
+    ``dvec, lam, f, grad, g, jac, hess`` are views into them."""
 
-    _FIELDS = (('dvec', 'ndec'), ('lam', 'ncons'), ('grad', 'ndec'),
-               ('g', 'ncons'), ('jac', 'nnz_jac'), ('hess', 'nnz_hess'))
+    _RESULTS = ('f', 'grad', 'g', 'jac', 'hess')
 
     def __init__(self, handle):
         self.handle = handle
-        self._pinned = {}
-        for name, size in self._FIELDS:
-            n = handle.batch * getattr(handle, size)
-            self._pinned[name] = PinnedArray(handle.lib, n)
-            setattr(self, name, self._pinned[name].array)
-        self._pinned['f'] = PinnedArray(handle.lib, handle.batch)
-        self.f = self._pinned['f'].array
+        h = handle
+        in_off, in_total, res_off, res_total = h.io_layout()
+        self._in = PinnedArray(h.lib, in_total)
+        self._res = PinnedArray(h.lib, res_total)
+        self.inputs, self.results = self._in.array, self._res.array
+        self.inputs[:] = 0.0
+        B = h.batch
+        self.dvec = self.inputs[in_off[0]:in_off[0] + B * h.ndec]
+        self.lam = self.inputs[in_off[1]:in_off[1] + B * h.ncons]
+        sizes = (B, B * h.ndec, B * h.ncons, B * h.nnz_jac, B * h.nnz_hess)
+        for name, off, n in zip(self._RESULTS, res_off, sizes):
+            setattr(self, name, self.results[off:off + n])
+
+    def upload(self, obj_factor=None):
+        """H2D of the decision vector (and, with ``obj_factor``, of the
+        multipliers) in one copy."""
+        if obj_factor is None:
+            self.handle.set_inputs(X, 0.0, self.inputs)
+        else:
+            self.handle.set_inputs(X | LAMBDA, obj_factor, self.inputs)
+
+    def fetch(self, which=ALL):
+        """D2H of the selected results in one copy, then synchronise."""
+        self.handle.fetch_results_async(which, self.results)
+        self.handle.synchronize()
 
     def fetch_all(self):
-        h = self.handle
-        for bit, name in ((F, 'f'), (GRAD, 'grad'), (G, 'g'), (JAC, 'jac'),
-                          (HESS, 'hess')):
-            if getattr(self, name).size:
-                h.fetch_async(bit, getattr(self, name))
-        h.synchronize()
+        self.fetch(ALL)
 
     def close(self):
-        for p in self._pinned.values():
-            p.close()
+        self.dvec = self.lam = self.inputs = self.results = None
+        for name in self._RESULTS:
+            setattr(self, name, None)
+        self._in.close()
+        self._res.close()
 
 
 class ProblemBackend:

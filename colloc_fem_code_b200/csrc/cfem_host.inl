@@ -50,6 +50,12 @@ struct cfem_problem {
     cfem::KArgs   k;
     double*       d_dvec = nullptr;     // owned copy of dvec (k.dvec may alias it)
     double*       d_lam = nullptr;
+    // inputs and results live in ONE device allocation each, so that a whole
+    // callback set moves with one H2D and one D2H copy (cfem_io_layout)
+    double*       d_inputs = nullptr;   // [dvec | lam]
+    double*       d_results = nullptr;  // [f | grad | g | jac | hess]
+    long long     in_off[2] = {0, 0}, in_total = 0;
+    long long     res_off[5] = {0, 0, 0, 0, 0}, res_len[5] = {0, 0, 0, 0, 0}, res_total = 0;
     double*       d_data[cfem::AtLeastOne<gen::kNumData>::value] = {};
     bool          have_dvec = false;
     bool          have_lam = false;
@@ -187,14 +193,9 @@ void cfem_destroy(cfem_problem* p)
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
-    cudaFree(p->d_dvec);
-    cudaFree(p->d_lam);
+    cudaFree(p->d_inputs);
+    cudaFree(p->d_results);
     for (int i = 0; i < gen::kNumData; ++i) cudaFree(p->d_data[i]);
-    cudaFree(p->k.f);
-    cudaFree(p->k.grad);
-    cudaFree(p->k.g);
-    cudaFree(p->k.jac);
-    cudaFree(p->k.hess);
     cudaFree(p->k.partials);
     cudaFree(p->k.done_count);
     cudaFree(p->k.group_count);
@@ -292,13 +293,28 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     CFEM_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     for (cudaEvent_t& e : p->ev) CFEM_TRY(cudaEventCreate(&e));
     for (cudaEvent_t& e : p->kev) CFEM_TRY(cudaEventCreate(&e));
-    CFEM_TRY(cudaMalloc(&p->d_dvec, B * L.ndec * D));
-    CFEM_TRY(cudaMalloc(&p->d_lam, B * (L.ncons > 0 ? L.ncons : 1) * D));
-    CFEM_TRY(cudaMalloc(&k.f, B * D));
-    CFEM_TRY(cudaMalloc(&k.grad, B * L.ndec * D));
-    CFEM_TRY(cudaMalloc(&k.g, B * (L.ncons > 0 ? L.ncons : 1) * D));
-    CFEM_TRY(cudaMalloc(&k.jac, B * (L.nnz_jac > 0 ? L.nnz_jac : 1) * D));
-    CFEM_TRY(cudaMalloc(&k.hess, B * (L.nnz_hess > 0 ? L.nnz_hess : 1) * D));
+    {
+        // segments start on 256-byte boundaries (32 doubles)
+        auto up = [](long long n) { return (n + 31) / 32 * 32; };
+        const long long in_len[2] = {(long long)B * L.ndec, (long long)B * L.ncons};
+        long long off = 0;
+        for (int i = 0; i < 2; ++i) { p->in_off[i] = off; off += up(in_len[i] > 0 ? in_len[i] : 1); }
+        p->in_total = off;
+        const long long rl[5] = {(long long)B, (long long)B * L.ndec, (long long)B * L.ncons,
+                                 (long long)B * L.nnz_jac, (long long)B * L.nnz_hess};
+        off = 0;
+        for (int i = 0; i < 5; ++i) { p->res_off[i] = off; p->res_len[i] = rl[i]; off += up(rl[i] > 0 ? rl[i] : 1); }
+        p->res_total = off;
+    }
+    CFEM_TRY(cudaMalloc(&p->d_inputs, (size_t)p->in_total * D));
+    CFEM_TRY(cudaMalloc(&p->d_results, (size_t)p->res_total * D));
+    p->d_dvec = p->d_inputs + p->in_off[0];
+    p->d_lam = p->d_inputs + p->in_off[1];
+    k.f = p->d_results + p->res_off[0];
+    k.grad = p->d_results + p->res_off[1];
+    k.g = p->d_results + p->res_off[2];
+    k.jac = p->d_results + p->res_off[3];
+    k.hess = p->d_results + p->res_off[4];
     CFEM_TRY(cudaMalloc(&k.partials, B * k.ntiles * gen::kNumDynReduce * D));
     CFEM_TRY(cudaMalloc(&k.reduce, B * gen::kNumReduce * D));
     CFEM_TRY(cudaMalloc(&k.gpartials, B * k.ngroups * gen::kNumDynReduce * D));
@@ -601,6 +617,59 @@ int cfem_fetch(cfem_problem* p, uint32_t which, double* host_out)
     int rc = cfem_fetch_async(p, which, host_out);
     if (rc) return rc;
     CFEM_CUDA(p, cudaStreamSynchronize(p->stream));
+    return CFEM_OK;
+}
+
+// Whole callback sets with ONE copy per direction: the host blocks mirror the
+// device slabs (cfem_io_layout), segment for segment.
+int cfem_io_layout(const cfem_problem* p, int64_t* in_off, int64_t* in_total,
+                   int64_t* res_off, int64_t* res_total)
+{
+    if (!p) return CFEM_EINVAL;
+    if (in_off) { in_off[0] = p->in_off[0]; in_off[1] = p->in_off[1]; }
+    if (in_total) *in_total = p->in_total;
+    if (res_off) for (int i = 0; i < 5; ++i) res_off[i] = p->res_off[i];
+    if (res_total) *res_total = p->res_total;
+    return CFEM_OK;
+}
+
+int cfem_set_inputs(cfem_problem* p, uint32_t which, double obj_factor, const double* host_inputs)
+{
+    if (!p || !host_inputs || !(which & (CFEM_X | CFEM_LAMBDA)) || (which & ~(CFEM_X | CFEM_LAMBDA)))
+        return CFEM_EINVAL;
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    const bool x = which & CFEM_X, l = (which & CFEM_LAMBDA) && p->k.ncons > 0;
+    const long long lo = x ? p->in_off[0] : p->in_off[1];
+    const long long hi = l ? p->in_off[1] + (long long)p->batch * p->k.ncons
+                           : p->in_off[0] + (long long)p->batch * p->k.ndec;
+    if (hi > lo)
+        CFEM_CUDA(p, cudaMemcpyAsync(p->d_inputs + lo, host_inputs + lo, (size_t)(hi - lo) * sizeof(double),
+                                     cudaMemcpyHostToDevice, p->stream));
+    if (x) { p->k.dvec = p->d_dvec; p->have_dvec = true; p->valid = 0; }
+    if (which & CFEM_LAMBDA) {
+        p->k.lam = p->d_lam;
+        p->k.obj_factor = obj_factor;
+        p->have_lam = true;
+        p->valid &= ~CFEM_HESS;
+    }
+    return CFEM_OK;
+}
+
+int cfem_fetch_results_async(cfem_problem* p, uint32_t which, double* host_results)
+{
+    if (!p || !host_results || !which || (which & ~CFEM_ALL)) return CFEM_EINVAL;
+    if ((p->valid & which) != which)
+        return cfem::fail(p, CFEM_ESTATE, "cfem_fetch_results: result not evaluated", cudaSuccess);
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    if (which & (CFEM_F | CFEM_GRAD)) { int rc = cfem_join_collect(p); if (rc) return rc; }
+    // one copy from the first requested segment to the end of the last one
+    int first = -1, last = -1;
+    for (int i = 0; i < 5; ++i)
+        if ((which >> i) & 1u) { if (first < 0) first = i; last = i; }
+    const long long lo = p->res_off[first], hi = p->res_off[last] + p->res_len[last];
+    if (hi > lo)
+        CFEM_CUDA(p, cudaMemcpyAsync(host_results + lo, p->d_results + lo, (size_t)(hi - lo) * sizeof(double),
+                                     cudaMemcpyDeviceToHost, p->stream));
     return CFEM_OK;
 }
 

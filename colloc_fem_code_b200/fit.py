@@ -282,12 +282,12 @@ class BatchFitter:
                         lv[i] = req[3]
                         want_all = True
                 t0 = time.perf_counter()
-                h.set_dvec(buf.dvec)
                 if want_all:
-                    h.set_multipliers(sigma, buf.lam)
+                    buf.upload(sigma)
                     h.eval(backend.ALL)
                     buf.fetch_all()
                 else:
+                    buf.upload()
                     h.eval(backend.F | backend.G)
                     h.fetch_async(backend.F, buf.f)
                     h.fetch_async(backend.G, buf.g)

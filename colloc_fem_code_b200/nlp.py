@@ -129,7 +129,7 @@ class GpuEvaluator(Evaluator):
 
     def _set_x(self, x):
         self.buf.dvec[:] = x
-        self.h.set_dvec(self.buf.dvec)
+        self.buf.upload()
 
     def eval_fg(self, x):
         t0 = time.perf_counter()
@@ -144,11 +144,11 @@ class GpuEvaluator(Evaluator):
 
     def eval_all(self, x, sigma, lam):
         t0 = time.perf_counter()
-        self._set_x(x)
+        self.buf.dvec[:] = x
         self.buf.lam[:] = lam
-        self.h.set_multipliers(sigma, self.buf.lam)
+        self.buf.upload(sigma)          # one H2D copy: [x | lambda]
         self.h.eval(backend.ALL)
-        self.buf.fetch_all()
+        self.buf.fetch_all()            # one D2H copy: [f | grad | g | jac | hess]
         self.seconds += time.perf_counter() - t0
         self.calls += 1
         b = self.buf

@@ -131,6 +131,22 @@ int          cfem_fetch(cfem_problem* p, uint32_t which, double* host_out);
 /* Same copy without the synchronisation (host_out should be pinned memory);
  * complete after cfem_synchronize(). */
 int          cfem_fetch_async(cfem_problem* p, uint32_t which, double* host_out);
+/* A whole callback set with ONE copy per direction.  Inputs [dvec | lambda]
+ * and results [f | grad | g | jac | hess] each live in one device allocation;
+ * cfem_io_layout gives the segment offsets (in doubles, 256-byte aligned) and
+ * the total sizes of host blocks that mirror them.  cfem_set_inputs copies
+ * the CFEM_X and/or CFEM_LAMBDA segment(s) of such a host block (and sets
+ * obj_factor with CFEM_LAMBDA); cfem_fetch_results_async copies the range
+ * from the first to the last requested result (a mask of CFEM_F..CFEM_HESS,
+ * all evaluated) into the host block.  Asynchronous on the handle's stream;
+ * the blocks should be page-locked (cfem_host_alloc). */
+int          cfem_io_layout(const cfem_problem* p, int64_t* in_off /*[2]*/,
+                            int64_t* in_total, int64_t* res_off /*[5]*/,
+                            int64_t* res_total);
+int          cfem_set_inputs(cfem_problem* p, uint32_t which, double obj_factor,
+                             const double* host_inputs);
+int          cfem_fetch_results_async(cfem_problem* p, uint32_t which,
+                                      double* host_results);
 /* Time-sharded problems behind ONE solver process: the decision vector, the
  * multipliers and the results live in shared page-locked host vectors in the
  * GLOBAL order; every rank moves only its own pieces, straight between that

@@ -351,3 +351,59 @@ def test_launch_variants_give_identical_bits(kind, dims, N, batch, monkeypatch):
         np.testing.assert_array_equal(np.ravel(np.asarray(a))[:np.size(b)]
                                       if batch > 1 else np.ravel(a),
                                       np.ravel(b))
+
+
+@pytest.mark.parametrize('batch', [1, 3])
+def test_single_copy_transfers(batch):
+    """cfem_set_inputs / cfem_fetch_results_async (one copy per direction
+    through host blocks that mirror the device slabs) against the per-array
+    calls, for full and partial result masks."""
+    nx, nu, ny, N = 2, 1, 2, 1001
+    cases = []
+    for b in range(batch):
+        exp = synthetic.experiment(60 + b, N, nx, nu, ny)
+        p = families.make_problem('ml', exp['y'], exp['u'], nx)
+        cases.append((p,) + synthetic.evaluation_point(p, exp, seed=b))
+    st = cases[0][0].structure
+    lib = backend.Library.for_structure(st)
+    data = [np.stack([c[0].structure.data[i]['source'] for c in cases])
+            for i in range(len(st.data))]
+    if batch == 1:
+        data = [d[0] for d in data]
+    h = backend.Handle(lib, N, data, st.scalar_values, batch=batch)
+    dvec = np.concatenate([c[1] for c in cases])
+    lam = np.concatenate([c[2] for c in cases])
+    in_off, in_total, res_off, res_total = h.io_layout()
+    assert all(o % 32 == 0 for o in in_off + res_off)
+    buf = backend.HostBuffers(h)
+    assert buf.inputs.size == in_total and buf.results.size == res_total
+    names = ('f', 'grad', 'g', 'jac', 'hess')
+    # reference: per-array calls
+    h.set_dvec(dvec)
+    h.set_multipliers(0.75, lam)
+    h.eval(backend.ALL)
+    ref = {n: h.fetch(1 << i).copy() for i, n in enumerate(names)}
+    # one copy each way
+    buf.dvec[:] = dvec
+    buf.lam[:] = lam
+    buf.results[:] = np.nan
+    buf.upload(0.75)
+    h.eval(backend.ALL)
+    buf.fetch_all()
+    for n in names:
+        np.testing.assert_array_equal(getattr(buf, n), np.ravel(ref[n]), n)
+    # x only, partial masks: the copied range spans first..last requested
+    buf.dvec[:] = dvec * 1.001
+    buf.upload()
+    h.eval(backend.F | backend.G)
+    buf.results[:] = np.nan
+    buf.fetch(backend.F | backend.G)
+    h.set_dvec(dvec * 1.001)
+    h.eval(backend.F | backend.G)
+    np.testing.assert_array_equal(buf.f, np.ravel(h.fetch(backend.F)))
+    np.testing.assert_array_equal(buf.g, np.ravel(h.fetch(backend.G)))
+    assert np.isnan(buf.jac).all() and np.isnan(buf.hess).all()
+    with pytest.raises(backend.CfemError):
+        buf.fetch(backend.HESS)             # not evaluated at this x
+    buf.close()
+    h.close()

@@ -97,8 +97,7 @@ def main():
             ts = []
             for i in range(30):
                 t0 = time.perf_counter()
-                h.set_dvec(host.dvec)
-                h.set_multipliers(sigma, host.lam)
+                host.upload(sigma)
                 h.eval(31)
                 host.fetch_all()
                 ts.append(time.perf_counter() - t0)
