@@ -580,39 +580,81 @@ class Generator:
         return f'lam[a.cons_off[{mult[1]}] + {mult[2]}]'
 
     @staticmethod
-    def _parse_flat(code):
-        """``code`` as a flat sum of products ``[(coeff, [identifier, ...])]``
-        in the printed order, or None if it is anything else (parentheses,
-        divisions, function calls).  ``a - b*c`` becomes ``+1*a`` and
-        ``-1*b*c``: sign flips are exact in IEEE arithmetic, so evaluating the
-        terms left to right reproduces the printed expression."""
+    def _split_top(text, seps):
+        """Split ``text`` at the top-level (outside parentheses) occurrences
+        of the separators; returns (pieces, separators)."""
+        pieces, used, depth, cur, i = [], [], 0, [], 0
+        while i < len(text):
+            ch = text[i]
+            if ch == '(':
+                depth += 1
+            elif ch == ')':
+                depth -= 1
+            hit = None
+            if depth == 0:
+                for sp in seps:
+                    if text.startswith(sp, i):
+                        hit = sp
+                        break
+            if hit:
+                pieces.append(''.join(cur))
+                used.append(hit)
+                cur = []
+                i += len(hit)
+            else:
+                cur.append(ch)
+                i += 1
+        pieces.append(''.join(cur))
+        return pieces, used
+
+    @classmethod
+    def _parse_sum(cls, code, allow_group=True):
+        """``code`` as a sum of products in the printed order:
+        ``[(coeff, [identifier, ...], inner)]`` where ``inner`` is None or the
+        parsed flat sum of ONE trailing parenthesised factor
+        (``c*a*b*(s1 + s2 + ...)``, the Horner-like form sympy prints for the
+        ZOH discretisation); None if the expression is anything else.
+        ``a - b*c`` becomes ``+1*a`` and ``-1*b*c``: sign flips are exact in
+        IEEE arithmetic, so evaluating terms and factors left to right
+        reproduces the printed expression operation for operation."""
         import re
-        if re.search(r'[()/]', code):
-            return None
-        toks = re.split(r'\s([+-])\s', code.strip())
-        terms, sign = [], 1.0
-        first = toks[0].strip()
-        if first.startswith('-'):
-            sign, first = -1.0, first[1:].strip()
-        toks[0] = first
-        i = 0
-        while i < len(toks):
-            body = toks[i]
-            facs = [t.strip() for t in body.split('*')]
-            coeff, idents = 1.0, []
+        num = r'[0-9]+(\.[0-9]*)?([eE][-+]?[0-9]+)?'
+        text = code.strip()
+        sign = 1.0
+        if text.startswith('-'):
+            sign, text = -1.0, text[1:].strip()
+        bodies, seps = cls._split_top(text, (' + ', ' - '))
+        terms = []
+        for i, body in enumerate(bodies):
+            if i > 0:
+                sign = 1.0 if seps[i - 1] == ' + ' else -1.0
+            facs, _ = cls._split_top(body.strip(), ('*',))
+            coeff, idents, inner = 1.0, [], None
             for k, t in enumerate(facs):
+                t = t.strip()
+                if inner is not None:
+                    return None         # the group must be the last factor
                 if re.fullmatch(r'v_[A-Za-z0-9_]+', t):
                     idents.append(t)
-                elif k == 0 and re.fullmatch(
-                        r'[0-9]+(\.[0-9]*)?([eE][-+]?[0-9]+)?', t):
+                elif k == 0 and re.fullmatch(num, t):
                     coeff = float(t)
+                elif k == 0 and re.fullmatch(rf'\(({num})/({num})\)', t):
+                    a_, b_ = t[1:-1].split('/')
+                    coeff = float(a_) / float(b_)   # folded by the C compiler too
+                elif (allow_group and t.startswith('(') and t.endswith(')')
+                      and k == len(facs) - 1 and k > 0):
+                    inner = cls._parse_sum(t[1:-1], allow_group=False)
+                    if inner is None:
+                        return None
                 else:
                     return None
-            terms.append((sign * coeff, idents))
-            if i + 1 < len(toks):
-                sign = 1.0 if toks[i + 1] == '+' else -1.0
-            i += 2
+            terms.append((sign * coeff, idents, inner))
         return terms
+
+    @classmethod
+    def _parse_flat(cls, code):
+        terms = cls._parse_sum(code, allow_group=False)
+        return None if terms is None else [(c, ids) for c, ids, _ in terms]
 
     #: entries per __noinline__ chunk function of the parameter kernel (ptxas
     #: time grows super-linearly with the size of one function)
@@ -630,8 +672,10 @@ class Generator:
         """The parameter-only constraints are polynomials of the parameters.
         Entries that print as a flat sum of products (over 90 % of them) go
         into a TABLE -- per entry a destination, a term range and an optional
-        multiplier (lambda / obj_factor); per term a coefficient and a factor
-        range -- evaluated by one uniform loop, a thread per (entry, problem):
+        multiplier (lambda / obj_factor); per term a coefficient, a factor
+        range and optionally the term range of ONE trailing parenthesised
+        factor (the Horner-like form of the ZOH discretisation) -- evaluated
+        by one uniform loop, a thread per (entry, problem):
         no per-entry code, no divergence, compile time and instruction-cache
         footprint independent of the number of entries.  The rest (nested,
         Horner-like expressions of the ZOH discretisation) keeps generated
@@ -641,28 +685,52 @@ class Generator:
         self.n_param_entries = len(order)
         table, code_ents = [], []
         for ent in order:
-            terms = self._parse_flat(ent['code'])
+            terms = self._parse_sum(ent['code'])
             if terms is None:
                 code_ents.append(ent)
                 continue
             idmap = {symoptim.c_ident(a_, fl): (a_, fl) for a_, fl in ent['deps']}
-            if any(i not in idmap for _, ids in terms for i in ids):
+            used = [i for _, ids, inner in terms
+                    for i in ids + [j for _, jds, _ in (inner or [])
+                                    for j in jds]]
+            if any(i not in idmap for i in used):
                 code_ents.append(ent)
                 continue
-            ent['terms'] = [(c, [self._pack_factor(ent['fun'], *idmap[i])
-                                 for i in ids]) for c, ids in terms]
+
+            def pack(ids, ent=ent, idmap=idmap):
+                return [self._pack_factor(ent['fun'], *idmap[i]) for i in ids]
+            ent['terms'] = [(c, pack(ids), None if inner is None else
+                             [(ci, pack(jds)) for ci, jds, _ in inner])
+                            for c, ids, inner in terms]
             table.append(ent)
         self.n_param_table, self.n_param_code = len(table), len(code_ents)
         CH = self.PARAM_CHUNK
         w = []
         # ---- tables
+        # terms of an entry are contiguous; the inner sums (terms of a
+        # trailing parenthesised factor) are stored after all entry terms
         term0, coeffs, fac0, facs, dests, mults = [0], [], [0], [], [], []
+        inner_of = []           # per term: None or list of inner terms
         for ent in table:
-            for c, fl in ent['terms']:
+            for c, fl, inner in ent['terms']:
                 coeffs.append(c)
                 facs += fl
                 fac0.append(len(facs))
+                inner_of.append(inner)
             term0.append(len(coeffs))
+        in0, in1 = [], []
+        for inner in list(inner_of):
+            if inner is None:
+                in0.append(-1)
+                in1.append(-1)
+                continue
+            in0.append(len(coeffs))
+            for c, fl in inner:
+                coeffs.append(c)
+                facs += fl
+                fac0.append(len(facs))
+            in1.append(len(coeffs))
+        for ent in table:
             assert ent['blk'] < 1024 and ent['off'] < (1 << 20)
             dests.append((ent['kind'] << 30) | (ent['blk'] << 20) | ent['off'])
             m = ent['mult']
@@ -692,6 +760,8 @@ class Generator:
         w += arr('unsigned', 'kPE_mult', mults, lambda v: f'{v}u')
         w += arr('double', 'kPT_coeff', coeffs, lambda v: repr(float(v)))
         w += arr('int', 'kPT_fac0', fac0, str)
+        w += arr('int', 'kPT_in0', in0, str)
+        w += arr('int', 'kPT_in1', in1, str)
         w += arr('unsigned', 'kPF', facs, lambda v: f'{v}u')
         # ---- generated code for the remaining entries
         nchunks = (len(code_ents) + CH - 1) // CH
@@ -751,15 +821,27 @@ class Generator:
         w.append('        const unsigned kind = dest >> 30;')
         w.append(f'        if (!(mask & ({G}u << kind))) return;')
         w.append('        const double* __restrict__ dvec = a.dvec + b * a.ndec;')
-        w.append('        double sum = 0.0;')
-        w.append('        for (int t = kPE_term0[e]; t < kPE_term0[e + 1]; ++t) {')
+        w.append('        // coefficient times factors, left to right (the printed '
+                 'order, no contraction)')
+        w.append('        auto product = [&](int t) {')
         w.append('            double p = kPT_coeff[t];')
         w.append('            for (int k = kPT_fac0[t]; k < kPT_fac0[t + 1]; ++k) {')
         w.append('                const unsigned f = kPF[k];')
         w.append('                const double v = (f >> 30) == 0u ? '
                  'dvec[a.var_off[(f >> 20) & 1023u] + (f & 0xFFFFFu)] '
                  ': a.scalars[(f >> 20) & 1023u];')
-        w.append('                p = __dmul_rn(p, v);     // printed order, no contraction')
+        w.append('                p = __dmul_rn(p, v);')
+        w.append('            }')
+        w.append('            return p;')
+        w.append('        };')
+        w.append('        double sum = 0.0;')
+        w.append('        for (int t = kPE_term0[e]; t < kPE_term0[e + 1]; ++t) {')
+        w.append('            double p = product(t);')
+        w.append('            if (kPT_in0[t] >= 0) {      // ... * (inner sum)')
+        w.append('                double inner = 0.0;')
+        w.append('                for (int u = kPT_in0[t]; u < kPT_in1[t]; ++u) '
+                 'inner = __dadd_rn(inner, product(u));')
+        w.append('                p = __dmul_rn(p, inner);')
         w.append('            }')
         w.append('            sum = __dadd_rn(sum, p);')
         w.append('        }')
