@@ -742,6 +742,11 @@ class Generator:
                 assert m[1] < 1024 and m[2] < (1 << 20)
                 mults.append((m[1] << 20) | m[2])
 
+        # kept for inspection / the CPU test of the table builder
+        self.param_table = dict(
+            entries=table, term0=term0, coeff=coeffs, fac0=fac0, fac=facs,
+            in0=in0, in1=in1, dest=dests, mult=mults)
+
         def arr(ctype, name, vals, fmt):
             body = ', '.join(fmt(v) for v in vals) if vals else fmt(0)
             lines = [f'static __device__ const {ctype} {name}'
