@@ -240,3 +240,39 @@ def test_pieces_cover_inputs_and_results():
                     c[g0:g0 + n] += 1
         for kind, c in seen.items():
             assert (c == 1).all(), (kind, world)
+
+
+def test_shared_vectors_backing_stores(monkeypatch):
+    """tmpfs file when /dev/shm has room, anonymous memfd (opened by the other
+    ranks through /proc/<pid>/fd) when it has not; the name disappears after
+    unlink() while the mappings stay valid."""
+    sizes = {k: 1000 for k in sharding.SharedVectors.FIELDS}
+    a = sharding.SharedVectors(sizes, 2)
+    assert a.path.startswith('/dev/shm/')
+    b = sharding.SharedVectors(sizes, 2, path=a.path)
+    a.jac[:] = 3.0
+    a.sigma = -1.5
+    assert (b.jac == 3.0).all() and b.sigma == -1.5
+    for name in sharding.SharedVectors.FIELDS:       # 64-byte aligned fields
+        assert getattr(a, name).ctypes.data % 64 == a.ctrl.ctypes.data % 64
+    path = a.path
+    a.unlink()
+    assert not os.path.exists(path)
+    b.hess[-1] = 7.0
+    assert a.hess[-1] == 7.0
+    a.close()
+    b.close()
+
+    class Full:
+        f_bavail, f_frsize = 1, 4096
+    monkeypatch.setattr(os, 'statvfs', lambda p: Full())
+    c = sharding.SharedVectors(sizes, 2)
+    assert c.path.startswith('/proc/')
+    d = sharding.SharedVectors(sizes, 2, path=c.path)
+    c.dvec[:] = 2.0
+    assert (d.dvec == 2.0).all()
+    c.unlink()
+    d.grad[0] = 1.0
+    assert c.grad[0] == 1.0
+    c.close()
+    d.close()
