@@ -523,8 +523,9 @@ int cfem_eval(cfem_problem* p, uint32_t what)
     const unsigned mask = cfem::pick_mask(what);
     if (!mask) return cfem::fail(p, CFEM_EINVAL, "cfem_eval: no kernel for this selector", cudaSuccess);
     CFEM_CUDA(p, cudaSetDevice(p->device));
-    // The parameter-only functions are independent of the per-sample pass:
-    // fork them onto the auxiliary stream so that they overlap it.
+    // The parameter-only functions are independent of the per-sample pass and
+    // overlap it: one CUDA graph, programmatic dependent launch on one stream,
+    // or fork/join over the auxiliary stream (see the three branches below).
     const bool params = gen::kNumParamEntries > 0 && !p->skip_param &&
                         (mask & (CFEM_G | CFEM_JAC | CFEM_HESS));
     const int slot = (int)(p->kev_count % cfem_problem::kTimingRing);

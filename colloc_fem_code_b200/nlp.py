@@ -28,6 +28,7 @@ import os
 import time
 
 import numpy as np
+import scipy.linalg as sla
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
@@ -373,10 +374,12 @@ class BorderedBandKKT:
             self._key = key
         inner, border = self.inner, self.border
         neg = None
+        self._factors = None
         try:
             Kb = K[inner]
             Kbb = Kb[:, inner]
             lu = spla.splu(Kbb.tocsc(), permc_spec='NATURAL')
+            Y = cpl = Kpb = None
             if len(border):
                 # only the border columns that touch the samples (the model
                 # parameters proper) need a banded solve
@@ -388,13 +391,20 @@ class BorderedBandKKT:
                 if len(cpl):
                     Y = lu.solve(Kbp_s[:, cpl].toarray())
                     S[:, cpl] -= Kpb @ Y
-                zb = lu.solve(rhs[inner])
-                zp = np.linalg.solve(S, rhs[border] - Kpb @ zb)
-                if len(cpl):
-                    zb = zb - Y @ zp[cpl]
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter('ignore', sla.LinAlgWarning)
+                    S_lu = sla.lu_factor(S)
             else:
                 S = np.zeros((0, 0))
-                zb, zp = lu.solve(rhs[inner]), np.zeros(0)
+                S_lu = None
+            # kept for further right-hand sides with the same matrix
+            # (iterative refinement): no second factorisation
+            self._factors = (K, lu, Y, cpl, Kpb, S_lu)
+            zb, zp = self._back_solve(rhs)
+            if not (np.all(np.isfinite(zb)) and np.all(np.isfinite(zp))):
+                self._factors = None
+                return None             # singular border complement
             if want_inertia:
                 neg = self._band_negative(Kbb)
                 if neg is not None and len(border):
@@ -409,6 +419,30 @@ class BorderedBandKKT:
         sol[inner], sol[border] = zb, zp
         return sol, K, neg
 
+    def _back_solve(self, rhs):
+        K, lu, Y, cpl, Kpb, S_lu = self._factors
+        inner, border = self.inner, self.border
+        zb = lu.solve(rhs[inner])
+        if S_lu is None:
+            return zb, np.zeros(0)
+        zp = sla.lu_solve(S_lu, rhs[border] - Kpb @ zb)
+        if Y is not None:
+            zb = zb - Y @ zp[cpl]
+        return zb, zp
+
+    def resolve(self, rhs):
+        """Solution for another right-hand side with the matrix of the latest
+        ``solve`` (its factors are reused), or None."""
+        if getattr(self, '_factors', None) is None:
+            return None
+        try:
+            zb, zp = self._back_solve(rhs)
+        except (RuntimeError, np.linalg.LinAlgError, ValueError):
+            return None
+        sol = np.empty(len(rhs))
+        sol[self.inner], sol[self.border] = zb, zp
+        return sol
+
 
 def _kkt_solve(solver, H, J, delta_w, delta_c, rhs, want_inertia=False):
     """(sol, inertia_ok) with one step of iterative refinement.
@@ -421,9 +455,13 @@ def _kkt_solve(solver, H, J, delta_w, delta_c, rhs, want_inertia=False):
     res = rhs - K @ sol
     if np.all(np.isfinite(res)) and np.linalg.norm(res) > \
             1e-13 * np.linalg.norm(rhs):
-        cor = solver.solve(H, J, delta_w, delta_c, res)
-        if cor is not None:
-            sol = sol + cor[0]
+        if hasattr(solver, 'resolve'):
+            cor = solver.resolve(res)           # same factors, new rhs
+        else:
+            cor = solver.solve(H, J, delta_w, delta_c, res)
+            cor = None if cor is None else cor[0]
+        if cor is not None and np.all(np.isfinite(cor)):
+            sol = sol + cor
     if not want_inertia or neg is None:
         return sol, None
     return sol, neg == J.shape[0]
