@@ -10,14 +10,20 @@ parameter-only functions -- of the ATTAS short-period maximum-likelihood
 problem ((nx, nu, ny) = (2, 1, 2), attas_sp_ml.py:79-87 of the reference) on a
 synthetic trajectory of N = 1e6 samples per GPU.  With more than one GPU the
 trajectory is N = 1e6 x n_gpus samples, split in time with a one-sample halo;
-the objective and the parameter block of the gradient are all-reduced with
-NCCL every step (weak scaling).
+the objective and the parameter block of the gradient are summed across GPUs
+every step INSIDE the per-sample kernel over NVLink peer memory (pipelined:
+the kernel of step k+1 finishes the sums of step k; CFEM_REDUCE=peer_sync
+makes every kernel wait for its own sums, CFEM_REDUCE=nccl uses an NCCL
+all-reduce plus a small kernel instead).  Weak scaling.
 
 ``value``  callback sets per second with inputs resident in HBM (events around
            every step on the launching stream, L2 flushed between steps);
            one "set" is normalised to N = 1e6 samples.
 ``e2e``    the same through the host API: decision vector and multipliers in
-           pinned host memory -> H2D -> kernels -> D2H of all five results.
+           pinned host memory -> one H2D copy -> kernels -> one D2H copy of
+           all five results; with more than one GPU through ONE solver-facing
+           process (sharding.SolverFacingEvaluator): every rank moves its own
+           slices of the global-order vectors in shared page-locked memory.
 ``roofline``      HBM roofline of the fused per-sample kernel (a first pass of
            the same K steps with CUDA events around that kernel alone).
 ``cpu_baseline``  the CPU oracle (NumPy restatement of the reference's
