@@ -420,7 +420,7 @@ class BorderedBandKKT:
         return sol, K, neg
 
     def _back_solve(self, rhs):
-        K, lu, Y, cpl, Kpb, S_lu = self._factors
+        _, lu, Y, cpl, Kpb, S_lu = self._factors
         inner, border = self.inner, self.border
         zb = lu.solve(rhs[inner])
         if S_lu is None:

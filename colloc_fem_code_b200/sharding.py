@@ -477,7 +477,7 @@ class SolverFacingEvaluator:
 
     def serve(self):
         """Ranks other than 0: execute requests until the solver stops."""
-        sv, ctrl = self.sv, self.sv.ctrl
+        ctrl = self.sv.ctrl
         seq = 0
         while True:
             self._wait(lambda: ctrl[0] != seq)
@@ -491,7 +491,7 @@ class SolverFacingEvaluator:
 
     def _request(self, request):
         """Rank 0: post, do the own share, wait for everybody."""
-        sv, ctrl = self.sv, self.sv.ctrl
+        ctrl = self.sv.ctrl
         self._seq += 1
         ctrl[1] = request
         ctrl[0] = self._seq             # published last (x86 store order)
