@@ -271,6 +271,40 @@ except Exception:       # pragma: no cover - numba is optional
     _bt_negative = _bt_negative_py
 
 
+def _sym_factor(S):
+    """Bunch-Kaufman ``S = L D L'`` (LAPACK dsytrf) of a dense symmetric
+    matrix: ``(ldu, piv, neg)`` for ``dsytrs`` plus the number of negative
+    eigenvalues (Sylvester: the inertia of the 1x1 / 2x2 blocks of D), ``neg``
+    None when D is numerically singular; None if the factorisation broke
+    down.  One O(n^3/3) pass instead of an LU for the solve and a full
+    eigenvalue decomposition for the inertia."""
+    if S.shape[0] == 0:
+        return np.zeros((0, 0)), np.zeros(0, dtype=np.int32), 0
+    lwork, _ = sla.lapack.dsytrf_lwork(S.shape[0], lower=1)     # blocked code
+    ldu, piv, info = sla.lapack.dsytrf(S, lower=1, lwork=max(1, int(lwork)))
+    if info != 0:
+        return None
+    d, sub = np.diag(ldu), np.diag(ldu, -1)
+    two = piv < 0                       # both rows of a 2x2 block are flagged
+    first = np.zeros(len(piv), dtype=bool)
+    k, n = 0, len(piv)
+    while k < n:                        # leading rows of the 2x2 blocks
+        if two[k]:
+            first[k] = True
+            k += 2
+        else:
+            k += 1
+    ev1 = d[~two]
+    lead = np.flatnonzero(first)
+    a, c, b = d[lead], d[lead + 1], sub[lead]
+    half, disc = 0.5 * (a + c), np.sqrt(0.25 * (a - c) ** 2 + b * b)
+    ev = np.concatenate([ev1, half - disc, half + disc])
+    if not np.all(np.isfinite(ev)) or \
+            np.min(np.abs(ev)) <= 1e-14 * max(1.0, np.max(np.abs(ev))):
+        return ldu, piv, None
+    return ldu, piv, int((ev < 0).sum())
+
+
 class BorderedBandKKT:
     """Host solver for the KKT systems of the filter-error problems.
 
@@ -391,10 +425,11 @@ class BorderedBandKKT:
                 if len(cpl):
                     Y = lu.solve(Kbp_s[:, cpl].toarray())
                     S[:, cpl] -= Kpb @ Y
-                import warnings
-                with warnings.catch_warnings():
-                    warnings.simplefilter('ignore', sla.LinAlgWarning)
-                    S_lu = sla.lu_factor(S)
+                # the border complement is symmetric up to rounding: ONE
+                # Bunch-Kaufman LDL^T serves the solve and the inertia
+                S_lu = _sym_factor(0.5 * (S + S.T))
+                if S_lu is None:
+                    return None         # singular border complement
             else:
                 S = np.zeros((0, 0))
                 S_lu = None
@@ -408,11 +443,7 @@ class BorderedBandKKT:
             if want_inertia:
                 neg = self._band_negative(Kbb)
                 if neg is not None and len(border):
-                    ev_ = np.linalg.eigvalsh(0.5 * (S + S.T))
-                    if np.min(np.abs(ev_)) <= 1e-14 * max(1.0, np.max(np.abs(ev_))):
-                        neg = None
-                    else:
-                        neg += int((ev_ < 0).sum())
+                    neg = None if S_lu[2] is None else neg + S_lu[2]
         except (RuntimeError, np.linalg.LinAlgError):
             return None
         sol = np.empty(n + m)
@@ -425,7 +456,10 @@ class BorderedBandKKT:
         zb = lu.solve(rhs[inner])
         if S_lu is None:
             return zb, np.zeros(0)
-        zp = sla.lu_solve(S_lu, rhs[border] - Kpb @ zb)
+        zp, info = sla.lapack.dsytrs(S_lu[0], S_lu[1], rhs[border] - Kpb @ zb,
+                                     lower=1)
+        if info != 0:
+            raise np.linalg.LinAlgError('dsytrs failed')
         if Y is not None:
             zb = zb - Y @ zp[cpl]
         return zb, zp
