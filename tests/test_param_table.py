@@ -104,3 +104,55 @@ def test_tables_reproduce_the_printed_expressions_bit_for_bit(kind, dims):
             (ent['kind'], ent['blk'], ent['off'])
         checked += 1
     assert checked == gen.n_param_table
+
+
+def test_parser_on_random_expressions():
+    """Random sums of products in the printed style (signs, literal
+    coefficients, repeated symbols, one trailing group): evaluating the parsed
+    form left to right equals Python's evaluation of the string, bit for bit."""
+    rng = np.random.default_rng(5)
+    names = [f'v_p{k}_{j}' for k in range(3) for j in range(4)]
+    env = {n: float(rng.normal()) for n in names}
+
+    def rand_term(group_ok):
+        parts = []
+        if rng.random() < 0.6:
+            parts.append(rng.choice(['0.5', '2.0', '1.0', '0.33333333333333331',
+                                     '(1.0/3.0)', '1e-3', '12.0']))
+        for _ in range(int(rng.integers(0 if parts else 1, 5))):
+            parts.append(str(rng.choice(names)))
+        if not parts:
+            parts.append(str(rng.choice(names)))
+        if group_ok and rng.random() < 0.4 and \
+                not parts[-1].startswith(('0', '1', '2', '(')):
+            inner = rand_sum(False)
+            parts.append('(' + inner + ')')
+        return '*'.join(parts)
+
+    def rand_sum(group_ok):
+        n = int(rng.integers(1, 6))
+        out = ('-' if rng.random() < 0.3 else '') + rand_term(group_ok)
+        for _ in range(n - 1):
+            out += (' + ' if rng.random() < 0.5 else ' - ') + rand_term(group_ok)
+        return out
+
+    def evaluate(terms):
+        total = 0.0
+        for c, ids, inner in terms:
+            p = c
+            for i in ids:
+                p = p * env[i]
+            if inner is not None:
+                p = p * evaluate(inner)
+            total = total + p
+        return total
+
+    parsed = 0
+    for _ in range(400):
+        code = rand_sum(True)
+        terms = G._parse_sum(code)
+        if terms is None:
+            continue
+        parsed += 1
+        assert evaluate(terms) == eval(code, {'__builtins__': {}}, env), code
+    assert parsed > 300
