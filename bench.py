@@ -19,11 +19,23 @@ all-reduce plus a small kernel instead).  Weak scaling.
 ``value``  callback sets per second with inputs resident in HBM (events around
            every step on the launching stream, L2 flushed between steps);
            one "set" is normalised to N = 1e6 samples.
+``value_sync``  (N > 1) the same with the synchronous exchange: every kernel
+           returns with its own reduced objective / gradient, which is what a
+           sequential NLP solver needs; ``value`` is the pipelined exchange.
+``reduce_check``  after the timed passes every rank compares its objective and
+           the sRp-diagonal entries of its gradient with the closed form
+           -1/2 sum en^2 - N sum log sRp_ii and -N / sRp_ii computed on the host
+           from the GLOBAL decision vector; a failure exits non-zero.
 ``e2e``    the same through the host API: decision vector and multipliers in
            pinned host memory -> one H2D copy -> kernels -> one D2H copy of
            all five results; with more than one GPU through ONE solver-facing
            process (sharding.SolverFacingEvaluator): every rank moves its own
            slices of the global-order vectors in shared page-locked memory.
+``e2e_solver_api``  (N = 1) the five IPOPT callbacks in IPOPT's order through
+           nlp.GpuEvaluator.ipopt_eval with caller-owned PAGEABLE NumPy arrays
+           for x, lambda, f, grad, g, Jacobian and Hessian values, a new x every
+           step; ``e2e_solver_api_pinned``: the same arrays page-locked once
+           (GpuEvaluator.pin), as a solver with stable buffers would.
 ``roofline``      HBM roofline of the fused per-sample kernel (a first pass of
            the same K steps with CUDA events around that kernel alone).
 ``cpu_baseline``  the CPU oracle (NumPy restatement of the reference's
@@ -240,7 +252,9 @@ def workload_config(world, reduce_mode='none'):
         'family': KIND, 'dims': list(DIMS),
         'n_samples_total': N_PER_GPU * world,
         'parallelism': 'single GPU' if world == 1 else
-        f'time-sharded x{world}, 1-sample halo, {how}',
+        f'time-sharded x{world}, 1-sample halo, {how}'
+        + ('; `value` = this pipelined exchange, `value_sync` = every kernel '
+           'waits for its own sums' if reduce_mode == 'peer' else ''),
         'l2': f'flushed between timed steps ({FLUSH_BYTES >> 20} MiB memset, '
               'outside the per-step events); working set per step '
               f'{algorithmic_bytes_per_sample(nx, nu, ny) * N_PER_GPU / 1e6:.0f}'
@@ -322,18 +336,11 @@ def run_ours(args, out):
     if world > 1:
         reduce_mode = os.environ.get('CFEM_REDUCE', 'peer')
         if reduce_mode in ('peer', 'peer_sync'):
-            try:
-                ev.enable_peer_reduce(pipelined=reduce_mode == 'peer')
-            except Exception as exc:        # no P2P / symmetric memory
-                print(f'rank {rank}: peer reduce unavailable ({exc!r}); '
-                      'using NCCL', file=sys.stderr)
+            # rank-local preparation, vote, then the rendezvous on all ranks
+            if not ev.agree_on_peer_reduce(pipelined=reduce_mode == 'peer'):
+                print(f'rank {rank}: peer reduce unavailable; using NCCL',
+                      file=sys.stderr)
                 reduce_mode = 'nccl'
-        flags = torch.tensor([reduce_mode.startswith('peer')],
-                             dtype=torch.int32, device=f'cuda:{local_rank}')
-        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-        if reduce_mode.startswith('peer') and int(flags.item()) == 0:
-            h.set_peers(0, 1, [], [])
-            reduce_mode = 'nccl'
 
     def device_step():
         h.set_dvec_device(d_dvec.data_ptr())      # "new x": invalidates
@@ -388,6 +395,16 @@ def run_ours(args, out):
     # throughput is taken from pass 2, the same K steps without them
     probe = timed_pass(True)
     timed = timed_pass(False)
+    timed_sync = None
+    if reduce_mode == 'peer':
+        # the mode a sequential solver can use: post AND collect in one launch
+        h.set_peer_mode(False)
+        timed_sync = timed_pass(False)
+    reduce_check = check_reduction(h, ev, problem, dvec, ldvec, world,
+                                   local_rank, dist if world > 1 else None,
+                                   torch)
+    if reduce_mode == 'peer':
+        h.set_peer_mode(True)
     kernel_ms = probe['kernel_ms']
     wall, host_enqueue = timed['wall'], timed['host_enqueue']
     launches, step_ms = timed['launches'], timed['step_ms']
@@ -400,11 +417,18 @@ def run_ours(args, out):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_gather(per_rank, mine)
     total_ms = float(total_ms.item())
+    sync_ms = None
+    if timed_sync is not None:
+        t = torch.tensor([sum(timed_sync['step_ms'])], dtype=torch.float64,
+                         device=f'cuda:{local_rank}')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sync_ms = float(t.item())
     per_rank = {'ms_per_step': [round(float(t[0]), 5) for t in per_rank],
                 'kernel_ms': [round(float(t[1]), 5) for t in per_rank]}
 
     # ---- end to end through the host API (pinned host buffers) ---------------
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = 30              # >= 30: min and median are reported too
+    e2e_step_s = []
     sfe = None
     if world > 1:
         # ONE solver-facing process (rank 0) in front of all shards: x, lambda
@@ -451,7 +475,9 @@ def run_ours(args, out):
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(e2e_steps):
-            e2e_step(2 + i)
+            t_step = time.perf_counter()
+            e2e_step(2 + i)             # ends with a stream synchronise
+            e2e_step_s.append(time.perf_counter() - t_step)
         e1.record()
         sync_all()
         e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64,
@@ -477,8 +503,10 @@ def run_ours(args, out):
                 sfe._request(request)
             t0 = time.perf_counter()
             for i in range(e2e_steps):
+                t_step = time.perf_counter()
                 sv.dvec[0] = dvec[0] + 1e-12 * (2 + i)
                 sfe._request(request)
+                e2e_step_s.append(time.perf_counter() - t_step)
             e2e_ms = 1e3 * (time.perf_counter() - t0)
             sfe.stop()
         else:
@@ -495,6 +523,16 @@ def run_ours(args, out):
                     'host wall clock on rank 0 around complete requests; '
                     'bytes are per rank; page-locked: ' + str(sfe.pinned))
         sfe.close()
+    solver_api = None
+    if world == 1:
+        res = {k: np.array(getattr(host, k)) for k in
+               ('f', 'grad', 'g', 'jac', 'hess')}
+        host.close()
+        solver_api = {
+            'pageable': solver_api_leg(problem, dvec, lam, sigma, e2e_steps,
+                                       False, res, 2 + e2e_steps - 1),
+            'pinned': solver_api_leg(problem, dvec, lam, sigma, e2e_steps,
+                                     True, res, 2 + e2e_steps - 1)}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -524,7 +562,10 @@ def run_ours(args, out):
                 'value': e2e_steps * world / (e2e_ms * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': e2e_h2d, 'd2h_bytes_per_step': e2e_d2h,
                 'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
+                'ms_per_step_min': 1e3 * min(e2e_step_s),
+                'ms_per_step_median': 1e3 * float(np.median(e2e_step_s)),
                 'note': e2e_note},
+            'reduce_check': reduce_check,
             'roofline': {
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak,
@@ -536,11 +577,112 @@ def run_ours(args, out):
                                'burst copy)',
                 'frac_of_nominal_8TBs': achieved / 8000.0},
         }
+        if sync_ms is not None:
+            line['value_sync'] = sets / (sync_ms * 1e-3)
+            line['ms_per_step_sync'] = sync_ms / args.steps
+        if solver_api is not None:
+            line['e2e_solver_api'] = solver_api['pageable']
+            line['e2e_solver_api_pinned'] = solver_api['pinned']
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline()
         out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if not reduce_check['ok']:
+        raise SystemExit(f'reduce_check failed: {reduce_check}')
+
+
+def check_reduction(h, ev, problem, dvec, ldvec, world, device, dist, torch):
+    """Every rank: the reduced objective and the sRp-diagonal gradient entries
+    it holds after the timed passes against the closed form computed on the
+    host from the GLOBAL decision vector (symfem.py:61-65, adfem.py:119), and
+    its en-block of the gradient (= -en, exact).  MAX / MIN over ranks."""
+    from colloc_fem_code_b200 import backend, models
+    h.synchronize()
+    f = float(h.fetch(backend.F)[0])
+    grad = h.fetch(backend.GRAD)
+    var = problem.variables(dvec)
+    en = var['en']
+    ny = en.shape[1]
+    diag = var['sRp_tril'][models.tril_diag(ny)]
+    n_total = en.shape[0]
+    f_ref = -0.5 * float(np.sum(en * en)) - n_total * float(np.log(diag).sum())
+    off = dict(zip(problem.structure.var_names, h.layout()['var_offset']))
+    lo = int(off['sRp_tril'])
+    g_srp = grad[lo:lo + var['sRp_tril'].size][models.tril_diag(ny)]
+    rel = max(abs(f - f_ref) / abs(f_ref),
+              float(np.max(np.abs(g_srp + n_total / diag) * diag / n_total)))
+    eo = int(off['en'])
+    n_en = ev.shard.n_local * ny
+    en_exact = bool(np.array_equal(grad[eo:eo + n_en],
+                                   -ldvec[eo:eo + n_en]))
+    ok = rel <= 1e-12 and en_exact
+    if dist is not None:
+        t = torch.tensor([rel, 0.0 if ok else 1.0, f], dtype=torch.float64,
+                         device=f'cuda:{device}')
+        gathered = [t.clone() for _ in range(world)]
+        dist.all_gather(gathered, t)
+        rel = max(float(g[0]) for g in gathered)
+        same_bits = all(float(g[2]) == float(gathered[0][2])
+                        for g in gathered)
+        ok = all(float(g[1]) == 0.0 for g in gathered) and same_bits
+    else:
+        same_bits = True
+    return {'ok': bool(ok), 'rel_err': rel, 'tol': 1e-12, 'f': f,
+            'f_closed_form': f_ref, 'grad_en_block_exact': en_exact,
+            'same_bits_on_all_ranks': same_bits, 'ranks': world,
+            'what': 'f and d f/d sRp_ii vs -1/2 sum en^2 - N sum log sRp_ii '
+                    'and -N/sRp_ii from the global dvec, every rank'}
+
+
+def solver_api_leg(problem, dvec, lam, sigma, steps, pinned, expect, last_i):
+    """IPOPT's callback sequence (eval_f, eval_grad_f, eval_g, eval_jac_g,
+    eval_h -- IpStdCInterface.h) through nlp.GpuEvaluator.ipopt_eval with
+    caller-owned NumPy arrays and a new x every step; wall clock (every
+    callback returns with its result in the caller's array)."""
+    from colloc_fem_code_b200 import backend, nlp
+    ev = nlp.GpuEvaluator(problem)
+    n, m = problem.ndec, problem.ncons
+    x, lam_a = np.array(dvec), np.array(lam)
+    out = {'f': np.empty(1), 'grad': np.empty(n), 'g': np.empty(m),
+           'jac': np.empty(problem.nnzjac), 'hess': np.empty(problem.nnzhess)}
+    if pinned:
+        ev.pin(x, lam_a, *[out[k] for k in ('grad', 'g', 'jac', 'hess')])
+
+    def step(i):
+        x[0] = dvec[0] + 1e-12 * i          # a new x every step
+        ev.ipopt_eval(backend.F, x, True, out['f'])
+        ev.ipopt_eval(backend.GRAD, x, False, out['grad'])
+        ev.ipopt_eval(backend.G, x, False, out['g'])
+        ev.ipopt_eval(backend.JAC, x, False, out['jac'])
+        ev.ipopt_eval(backend.HESS, x, False, out['hess'], sigma, lam_a)
+
+    for i in range(2):
+        step(i)
+    times = []
+    t0 = time.perf_counter()
+    for i in range(steps):
+        t1 = time.perf_counter()
+        step(last_i - steps + 1 + i)
+        times.append(time.perf_counter() - t1)
+    total = time.perf_counter() - t0
+    # the last step used the same x as the last step of the C-ABI leg
+    for k in ('f', 'grad', 'g', 'jac', 'hess'):
+        np.testing.assert_allclose(out[k], expect[k], rtol=1e-12, atol=1e-300,
+                                   err_msg=f'e2e_solver_api: {k}')
+    groups = ev.kernel_groups
+    ev.close()
+    return {'value': steps / total, 'unit': UNIT,
+            'h2d_bytes_per_step': int(8 * (n + m)),
+            'd2h_bytes_per_step': int(8 * (1 + n + m + problem.nnzjac
+                                           + problem.nnzhess)),
+            'ms_per_step': 1e3 * total / steps, 'steps': steps,
+            'ms_per_step_min': 1e3 * min(times),
+            'ms_per_step_median': 1e3 * float(np.median(times)),
+            'kernel_groups_per_step': groups / (steps + 2),
+            'host_arrays': 'page-locked once (GpuEvaluator.pin)' if pinned
+            else 'pageable NumPy (threaded staging inside the C ABI)',
+            'checked_against_c_abi_leg': True}
 
 
 def ncu_traffic():

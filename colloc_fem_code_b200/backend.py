@@ -126,6 +126,8 @@ ABI = {
     'cfem_host_free': (None, [ctypes.c_void_p]),
     'cfem_host_register': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
     'cfem_host_unregister': (ctypes.c_int, [ctypes.c_void_p]),
+    'cfem_store_release_i64': (None, [ctypes.c_void_p, ctypes.c_int64]),
+    'cfem_load_acquire_i64': (ctypes.c_int64, [ctypes.c_void_p]),
 }
 
 

@@ -385,13 +385,15 @@ class Generator:
                     w += undefs
             w.append('    }')
 
-        def stage(tile_expr, buf_expr):
-            """cp.async of one tile's rows into staging buffer buf_expr."""
+        def stage(it_expr, buf_expr):
+            """cp.async of the rows of this CTA's tile ``it_expr`` into
+            staging buffer ``buf_expr``."""
             out = ['        {',
                    f'            double* const stg = smem + '
                    f'{lay["stage_off"]} + ({buf_expr}) * {lay["stage_stride"]};',
-                   f'            const long long r0 = ({tile_expr}) * {T};',
-                   '            (void)stg; (void)r0;']
+                   f'            const long long r0 = CFEM_TILE_K0({it_expr});',
+                   f'            const int nr = 32 * CFEM_TILE_NW({it_expr});',
+                   '            (void)stg; (void)r0; (void)nr;']
             for key in sorted(lay['stor']):
                 st_ = lay['stor'][key]
                 if key[0] == 'var':
@@ -407,81 +409,103 @@ class Generator:
                     rows = f'a.fun_rows[{key[1]}]'
                 out.append(f'            cfem::stage_rows_async<{st_["core"]}, '
                            f'{st_["nrows"]}>(stg + {st_["off"]}, {src}, '
-                           f'{rows}, r0, tid);')
+                           f'{rows}, r0, nr + {st_["shift"]}, tid);')
             out.append('        }')
             return out
 
-        def prefetch(tile_expr):
-            out = ['        {',
-                   f'            const long long r0 = ({tile_expr}) * {T};']
-            for key in sorted(lay['stor']):
-                st_ = lay['stor'][key]
-                if key[0] == 'var':
-                    src = f'dvec + a.var_off[{key[1]}]'
-                    rows = f'a.var_rows[{key[1]}]'
-                elif key[0] == 'data':
-                    src = (f'a.data[{key[1]}] + b * a.data_rows[{key[1]}] * '
-                           f'{st_["core"]}')
-                    rows = f'a.data_rows[{key[1]}]'
-                else:
-                    ci = self.funs[key[1]]['cons_index']
-                    src = f'a.lam + b * a.ncons + a.cons_off[{ci}]'
-                    rows = f'a.fun_rows[{key[1]}]'
-                out.append(f'            cfem::prefetch_rows_l2<{st_["core"]}, '
-                           f'{st_["nrows"]}>({src}, {rows}, r0, tid);')
-            out.append('        }')
-            return out
+        has_red = bool(mask & (F | GRAD))
+        # the reduction runs right after the last function that feeds it, in
+        # the CTA's LAST tile, i.e. BEFORE the bulk of that tile's stores: its
+        # fence then has no store queue to drain and the serial tail of the
+        # grid-wide tree (and of the cross-GPU exchange) overlaps the stores
+        red_after = max([i for i, p in enumerate(plan) if p['reds']],
+                        default=-1) if has_red else -1
+        reduce_call = [
+            f'        if (cfem::tree_reduce<{max(nred, 1)}>(a, b, red, smem + '
+            f'{lay["red_off"]}, tid)) {{',
+            '            // this CTA retired last: it finalises (fixed '
+            'summation tree => deterministic)',
+            f'            cfem_finalize(a, {mask}u, b, tid, smem + '
+            f'{lay["red_off"]});',
+            '            if (tid == 0) a.done_count[b] = 0u;',
+            '        }']
 
-        # persistent CTAs: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the
-        # inputs of the next tile are in flight (cp.async) while this one is
-        # evaluated and streamed out
-        w.append('    const long long tstride = gridDim.x;')
-        w.append('    long long tile = blockIdx.x;')
+        # Balanced persistent schedule (cfem_args.cuh): `rounds` full tiles
+        # it * gridDim.x + blockIdx.x, then one partial tile of tail_n
+        # warp-rows; the inputs of the next tile are in flight (cp.async)
+        # while this one is evaluated and streamed out.
+        w.append('    const long long G = gridDim.x, c = blockIdx.x;')
+        w.append('    const int tail_n = a.tail_q + (c < a.tail_rem ? 1 : 0);')
+        w.append('    const long long tail_k0 = (a.tail_base + c * a.tail_q + '
+                 '(c < a.tail_rem ? c : (long long)a.tail_rem)) * 32;')
+        w.append('    const int nit = (int)a.rounds + (tail_n > 0 ? 1 : 0);')
+        w.append(f'#define CFEM_TILE_K0(it) ((it) < a.rounds ? ((it) * G + c) '
+                 f'* {T} : tail_k0)')
+        w.append(f'#define CFEM_TILE_NW(it) ((it) < a.rounds ? {T // 32} : '
+                 'tail_n)')
         w.append('    int buf = 0;')
-        w.append('    if (tile < a.ntiles)')
-        w += stage('tile', '0')
+        w.append('    if (nit > 0)')
+        w += stage('0', '0')
         w.append('    cfem::cp_async_commit();')
-        w.append('    if (a.prefetch_tiles > 0 && tile + a.prefetch_tiles < a.ntiles)')
-        w += prefetch('tile + a.prefetch_tiles')
-        w.append('    for (; tile < a.ntiles; tile += tstride, buf ^= 1) {')
-        w.append('    if (tile + tstride < a.ntiles)')
-        w += stage('tile + tstride', 'buf ^ 1')
+        w.append('    for (int it = 0; it < nit; ++it, buf ^= 1) {')
+        w.append('    if (it + 1 < nit)')
+        w += stage('it + 1', 'buf ^ 1')
         w.append('    cfem::cp_async_commit();')
         w.append('    cfem::cp_async_wait<1>();      // this tile has landed')
         w.append('    __syncthreads();')
         w.append(f'    double* const stg = smem + {lay["stage_off"]} + buf * '
                  f'{lay["stage_stride"]};')
-        w.append(f'    const long long k0 = tile * {T};')
+        w.append('    const long long k0 = CFEM_TILE_K0(it);')
+        w.append('    const long long kend = k0 + 32 * CFEM_TILE_NW(it);')
         w.append('    const long long kw = k0 + warp * 32;')
         w.append('    const long long k = k0 + tid;')
-        w.append('    (void)stg; (void)kw; (void)k;')
+        w.append('    (void)stg; (void)kw; (void)k; (void)kend;')
         for key in sorted(lay['stor']):
             st_ = lay['stor'][key]
             w.append(f'    const double* const {st_["name"]} = stg + '
                      f'{st_["off"]};')
-        for p in plan:
+        for pi, p in enumerate(plan):
             fi = p['fi']
             f = self.funs[fi]
-            w.append(f'    // ---- {f["name"]}')
-            w.append('    {')
-            w.append(f'        const long long M = a.fun_rows[{fi}];')
-            w.append('        const long long left = M - kw;')
-            w.append('        const int nvalid = left >= 32 ? 32 : '
-                     '(left > 0 ? (int)left : 0);')
-            w.append('        const bool act = k < M;')
-            w.append('        (void)act;')
-            w.append('        if (nvalid > 0) {')
             defs, undefs = self._define_args(f, p['deps'], 'sample', lay)
-            w += ['        ' + d if d.startswith('#') else '            ' + d
-                  for d in defs]
+
+            def open_block():
+                w.append('    {')
+                w.append(f'        const long long M = a.fun_rows[{fi}] < kend'
+                         f' ? a.fun_rows[{fi}] : kend;')
+                w.append('        const long long left = M - kw;')
+                w.append('        const int nvalid = left >= 32 ? 32 : '
+                         '(left > 0 ? (int)left : 0);')
+                w.append('        const bool act = k < M;')
+                w.append('        (void)act;')
+                w.append('        if (nvalid > 0) {')
+                w.extend('        ' + d if d.startswith('#')
+                         else '            ' + d for d in defs)
+
+            def close_block():
+                w.extend('        ' + u for u in undefs)
+                w.append('        }')
+                w.append('    }')
+
+            w.append(f'    // ---- {f["name"]}')
+            if p['reds']:
+                open_block()
+                for slot, code in p['reds']:
+                    w.append(f'            red[{self.dyn_index[slot]}] += '
+                             f'act ? ({code}) : 0.0;')
+                close_block()
+            if pi == red_after:
+                w.append('    if (it + 1 == nit) {')
+                w += reduce_call
+                w.append('    }')
+            if not (p['items'] or p['uniform']):
+                continue
+            open_block()
             if p['lam']:
                 s = lay['stor'][('lam', fi)]
                 for o in range(f['out_core']):
                     w.append(f'            const double lam_{fi}_{o} = '
                              f'{s["name"]}[cfem::Skew<{s["core"]}>::row(tid) + {o}];')
-            for slot, code in p['reds']:
-                w.append(f'            red[{self.dyn_index[slot]}] += '
-                         f'act ? ({code}) : 0.0;')
             for it in p['uniform']:
                 w.append(f'            cfem::warp_store_periodic<{it.c}>(pat + '
                          f'{it.pat_off}, lane, ({it.dest}) + kw * {it.c}, '
@@ -515,21 +539,28 @@ class Generator:
                                  f'{wboff}, lane, ({it.dest}) + kw * {it.c}, '
                                  'nvalid);')
                     w.append('            __syncwarp();')
-            w += ['        ' + u for u in undefs]
-            w.append('        }')
-            w.append('    }')
-        w.append('    __syncthreads();       // staging buffer is refilled '
-                 'by the next prefetch')
+            close_block()
+        w.append('    if (it + 1 < nit) __syncthreads();   // staging buffer '
+                 'is refilled by the next prefetch')
         w.append('    }   // tile loop')
-        if mask & (F | GRAD):
-            w.append(f'    if (cfem::tree_reduce<{max(nred, 1)}>(a, b, red, smem + '
-                     f'{lay["red_off"]}, tid)) {{')
-            w.append('        // this CTA retired last: it finalises (fixed '
-                     'summation tree => deterministic)')
-            w.append(f'        cfem_finalize(a, {mask}u, b, tid, smem + '
-                     f'{lay["red_off"]});')
-            w.append('        if (tid == 0) a.done_count[b] = 0u;')
+        if has_red:
+            # CTAs without a tile, and kernels whose reductions have no
+            # per-sample term, still take part in the tree
+            if red_after >= 0:
+                w.append('    if (nit == 0) {')
+            else:
+                w.append('    {')
+            w += reduce_call
             w.append('    }')
+        w.append('#undef CFEM_TILE_K0')
+        w.append('#undef CFEM_TILE_NW')
+        w.append('    // programmatic dependent launch: the parameter-only '
+                 'kernel is the prerequisite grid;')
+        w.append('    // nothing here reads its results, but a completed '
+                 'per-sample kernel must imply a')
+        w.append('    // completed (and flushed) parameter-only kernel for '
+                 'whatever follows in the stream')
+        w.append('    asm volatile("griddepcontrol.wait;" ::: "memory");')
         w.append('}')
         return '\n'.join(w), lay['total'] * 8
 
@@ -1152,35 +1183,44 @@ class Generator:
                  'g_single_buf = atoi(v) != 0;')
         w.append('    return e;')
         w.append('}')
-        w.append('// Persistent launch: at most `max_ctas` CTAs per problem '
-                 '(resident CTAs per SM x SMs x waves), each looping over tiles.')
+        w.append('// Balanced persistent launch: one resident set of CTAs per '
+                 'problem (x `waves`), every CTA')
+        w.append('// gets the same number of 32-sample warp-rows to within one '
+                 '(cfem_args.cuh).  The CTA')
+        w.append('// count is the same for every kernel variant of the library '
+                 '(the smallest residency),')
+        w.append('// so the fixed-order reductions give the same bits whichever '
+                 'variant serves a callback.')
         w.append('// When that covers every tile (one tile per CTA) the second '
                  'staging buffer is')
         w.append('// not allocated: less shared memory per CTA, more resident '
                  'CTAs per SM.')
         w.append('static void prepare_sample(unsigned mask, int batch, '
-                 'int sm_count, int waves, long long prefetch, '
+                 'int sm_count, int waves, '
                  'cfem::KArgs& a, dim3& grid, size_t& smem)')
         w.append('{')
-        w.append('    int idx = 0;')
-        w.append('    for (int i = 0; i < kNumMasks; ++i) '
-                 'if (kMasks[i] == mask) idx = i;')
-        w.append('    int per_sm = g_ctas_per_sm1[idx];')
-        w.append('    long long gx = (long long)per_sm * sm_count * waves / batch;')
+        w.append('    int idx = 0, per_sm1 = 1 << 30, per_sm2 = 1 << 30;')
+        w.append('    for (int i = 0; i < kNumMasks; ++i) {')
+        w.append('        if (kMasks[i] == mask) idx = i;')
+        w.append('        if (g_ctas_per_sm1[i] < per_sm1) per_sm1 = g_ctas_per_sm1[i];')
+        w.append('        if (g_ctas_per_sm[i] < per_sm2) per_sm2 = g_ctas_per_sm[i];')
+        w.append('    }')
+        w.append('    long long gx = (long long)per_sm1 * sm_count * waves / batch;')
         w.append('    smem = kSmem1[idx];')
         w.append('    if (!g_single_buf || gx < a.ntiles) {     '
-                 '// persistent CTAs: double buffering')
-        w.append('        per_sm = g_ctas_per_sm[idx];')
-        w.append('        gx = (long long)per_sm * sm_count * waves / batch;')
+                 '// several tiles per CTA: double buffering')
+        w.append('        gx = (long long)per_sm2 * sm_count * waves / batch;')
         w.append('        smem = kSmem2[idx];')
         w.append('    }')
         w.append('    if (gx < 1) gx = 1;')
         w.append('    if (gx > a.ntiles) gx = a.ntiles;')
         w.append('    a.nctas = gx;')
-        w.append('    // CTAs that start one "resident set" later find their inputs in L2')
-        w.append('    a.prefetch_tiles = prefetch < 0 ? (long long)per_sm * sm_count '
-                 '/ batch : prefetch;')
-        w.append('    if (gx < a.ntiles) a.prefetch_tiles = 0;   // persistent: cp.async double buffering instead')
+        w.append('    const long long wpt = CFEM_TILE / 32, wr = (a.N + 31) / 32;')
+        w.append('    a.rounds = wr / (gx * wpt);')
+        w.append('    a.tail_base = a.rounds * gx * wpt;')
+        w.append('    const long long left = wr - a.tail_base;    // < gx * wpt')
+        w.append('    a.tail_q = (int)(left / gx);')
+        w.append('    a.tail_rem = (int)(left % gx);')
         w.append('    a.ngroups = (gx + cfem::kReduceGroup - 1) / '
                  'cfem::kReduceGroup;')
         w.append('    grid = dim3((unsigned)gx, (unsigned)batch);')
@@ -1191,12 +1231,12 @@ class Generator:
                  'no data dependence)')
         w.append('// is still running.')
         w.append('static cudaError_t launch_sample(unsigned mask, int batch, '
-                 'int sm_count, int waves, long long prefetch, bool overlap_prev, '
+                 'int sm_count, int waves, bool overlap_prev, '
                  'cudaStream_t s, cfem::KArgs a)')
         w.append('{')
         w.append('    cudaLaunchConfig_t cfg = {};')
         w.append('    size_t smem = 0;')
-        w.append('    prepare_sample(mask, batch, sm_count, waves, prefetch, a, cfg.gridDim, smem);')
+        w.append('    prepare_sample(mask, batch, sm_count, waves, a, cfg.gridDim, smem);')
         w.append('    cfg.dynamicSmemBytes = smem;')
         w.append('    cfg.blockDim = dim3(CFEM_TILE);')
         w.append('    cfg.stream = s;')

@@ -31,7 +31,14 @@ struct KArgs {
     double* partials;       // [batch][ntiles][nreduce]
     // two-level deterministic reduction tree (all counters zero between launches)
     long long     nctas;        // CTAs per problem of this launch (<= ntiles)
-    long long     prefetch_tiles;   // L2 prefetch distance in tiles (0: off)
+    // Balanced persistent schedule in units of warp-rows (32 samples): CTA c
+    // runs `rounds` full tiles (it * nctas + c) and then ONE partial tile of
+    // tail_q (+1 for c < tail_rem) warp-rows, so that every CTA of a problem
+    // gets the same number of samples to within one warp-row and the CTAs
+    // retire together (no half-empty last wave, no drain).
+    long long     rounds;       // full tiles per CTA
+    long long     tail_base;    // first warp-row of the partial tiles
+    int           tail_q, tail_rem;
     long long     ngroups;      // ceil(nctas / kReduceGroup)
     double*       gpartials;    // [batch][ngroups][nreduce]
     unsigned int* group_count;  // [batch][ngroups] CTAs retired per group

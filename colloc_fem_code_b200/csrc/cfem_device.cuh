@@ -114,32 +114,16 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory");
 }
 
-// Pull the rows a later tile will stage into L2 (one prefetch per 128-byte
-// line), so that its cp.async requests hit L2 instead of waiting on HBM behind
-// the store traffic.
-template <int CORE, int NROWS>
-__device__ __forceinline__ void prefetch_rows_l2(const double* __restrict__ src,
-                                                 long long rows_total,
-                                                 long long row_begin, int tid)
-{
-    long long lo = row_begin < 0 ? 0 : row_begin;
-    long long hi = row_begin + NROWS;
-    if (hi > rows_total) hi = rows_total;
-    if (hi <= lo) return;
-    const double* __restrict__ s = src + lo * CORE;
-    const int nelem = (int)(hi - lo) * CORE;
-    for (int e = tid * 16; e < nelem; e += CFEM_TILE * 16)
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(s + e));
-}
-
 template <int CORE, int NROWS>
 __device__ __forceinline__ void stage_rows_async(double* __restrict__ dst,
                                                  const double* __restrict__ src,
                                                  long long rows_total,
-                                                 long long row_begin, int tid)
+                                                 long long row_begin, int nrows,
+                                                 int tid)
 {
+    // nrows <= NROWS: a partial tile stages only the rows it evaluates
     long long lo = row_begin < 0 ? 0 : row_begin;
-    long long hi = row_begin + NROWS;
+    long long hi = row_begin + nrows;
     if (hi > rows_total) hi = rows_total;
     if (hi <= lo) return;
     const int first = (int)(lo - row_begin) * CORE;

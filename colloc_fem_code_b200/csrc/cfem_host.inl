@@ -12,16 +12,91 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cfem.h"
 
+namespace cfem {
+
+// Parallel memcpy between pageable and page-locked host memory.  The solver
+// (IPOPT) owns x / lambda / g / grad_f / values as ordinary pageable arrays; the
+// DMA engines need page-locked memory.  One host thread copies ~10 GB/s, the
+// PCIe link moves ~55 GB/s, so the staging copy is sliced over a few persistent
+// worker threads and pipelined chunk by chunk against the DMA transfers
+// (staged_d2h / staged_h2d below).
+class CopyPool {
+public:
+    explicit CopyPool(int nthreads) : n_(nthreads < 1 ? 1 : nthreads)
+    {
+        for (int i = 1; i < n_; ++i) workers_.emplace_back([this, i] { loop(i); });
+    }
+    ~CopyPool()
+    {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    int threads() const { return n_; }
+    // blocks until all slices are copied (the caller copies slice 0)
+    void copy(void* dst, const void* src, size_t bytes)
+    {
+        if (n_ == 1 || bytes < (size_t)(1 << 20)) { memcpy(dst, src, bytes); return; }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes;
+            pending_ = n_ - 1;
+            ++gen_;
+        }
+        cv_.notify_all();
+        slice(0);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+private:
+    void slice(int i)
+    {
+        const size_t per = ((bytes_ + n_ - 1) / n_ + 4095) & ~(size_t)4095;
+        const size_t lo = per * i;
+        if (lo >= bytes_) return;
+        const size_t len = bytes_ - lo < per ? bytes_ - lo : per;
+        memcpy(dst_ + lo, src_ + lo, len);
+    }
+    void loop(int i)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            slice(i);
+            std::lock_guard<std::mutex> lk(m_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    char* dst_ = nullptr; const char* src_ = nullptr; size_t bytes_ = 0;
+    int pending_ = 0;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+};
+
+}  // namespace cfem
+
 struct cfem_problem {
     int           device = 0;
     int           sm_count = 1;
-    int           waves = 8;            // CTAs launched <= resident CTAs x waves (B200 sweep)
-    long long     prefetch = 0;         // L2 prefetch distance in tiles; < 0: one resident set
+    int           waves = 1;            // CTAs launched <= resident CTAs x waves (balanced persistent schedule)
     cudaStream_t  stream = nullptr;
     bool          own_stream = false;
     cudaStream_t  aux_stream = nullptr;     // parameter-only kernel, concurrent
@@ -68,6 +143,14 @@ struct cfem_problem {
     long long     launches = 0;
     void*         flush_buf = nullptr;
     size_t        flush_bytes = 0;
+    // staging of pageable host arrays (allocated on first use)
+    static constexpr int kBounce = 4;
+    size_t        bounce_bytes = 8u << 20;      // CFEM_COPY_CHUNK_MB
+    int           copy_threads = 8;             // CFEM_COPY_THREADS
+    char*         bounce[kBounce] = {};
+    cudaEvent_t   bev[kBounce] = {};
+    cfem::CopyPool* pool = nullptr;
+    long long     staged_bytes = 0;             // moved through the bounce buffers so far
     std::string   err;
 };
 
@@ -162,6 +245,93 @@ static unsigned pick_mask(unsigned what)
     return best;
 }
 
+// true if `ptr` is host memory the DMA engines can address directly
+// (cudaHostAlloc / cudaHostRegister), false for ordinary pageable memory
+static bool host_is_pinned(const void* ptr)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+static int ensure_bounce(cfem_problem* p)
+{
+    if (p->pool) return CFEM_OK;
+    for (int i = 0; i < cfem_problem::kBounce; ++i) {
+        CFEM_CUDA(p, cudaHostAlloc((void**)&p->bounce[i], p->bounce_bytes, cudaHostAllocDefault));
+        CFEM_CUDA(p, cudaEventCreateWithFlags(&p->bev[i], cudaEventDisableTiming));
+    }
+    p->pool = new (std::nothrow) CopyPool(p->copy_threads);
+    if (!p->pool) return fail(p, CFEM_ENOMEM, "copy pool", cudaSuccess);
+    return CFEM_OK;
+}
+
+// device -> pageable host: DMA chunk i into a page-locked bounce buffer while
+// the worker threads copy chunk i-1.. out of the other bounce buffers.
+// Returns with the data in `dst` (synchronous, like cudaMemcpy to pageable
+// memory, but at several times its rate).
+static int staged_d2h(cfem_problem* p, void* dst, const void* dev_src, size_t bytes)
+{
+    { int rc = ensure_bounce(p); if (rc) return rc; }
+    constexpr int K = cfem_problem::kBounce;
+    const size_t C = p->bounce_bytes;
+    const size_t n = (bytes + C - 1) / C;
+    auto issue = [&](size_t i) -> cudaError_t {
+        const size_t off = i * C, len = bytes - off < C ? bytes - off : C;
+        cudaError_t e = cudaMemcpyAsync(p->bounce[i % K], (const char*)dev_src + off, len,
+                                        cudaMemcpyDeviceToHost, p->stream);
+        return e != cudaSuccess ? e : cudaEventRecord(p->bev[i % K], p->stream);
+    };
+    for (size_t i = 0; i < n && i < (size_t)K; ++i) CFEM_CUDA(p, issue(i));
+    for (size_t i = 0; i < n; ++i) {
+        const size_t off = i * C, len = bytes - off < C ? bytes - off : C;
+        CFEM_CUDA(p, cudaEventSynchronize(p->bev[i % K]));
+        p->pool->copy((char*)dst + off, p->bounce[i % K], len);
+        if (i + K < n) CFEM_CUDA(p, issue(i + K));
+    }
+    p->staged_bytes += (long long)bytes;
+    return CFEM_OK;
+}
+
+// pageable host -> device; the copies are enqueued on the handle's stream, the
+// source may be reused when the call returns.
+static int staged_h2d(cfem_problem* p, void* dev_dst, const void* src, size_t bytes)
+{
+    { int rc = ensure_bounce(p); if (rc) return rc; }
+    constexpr int K = cfem_problem::kBounce;
+    const size_t C = p->bounce_bytes;
+    const size_t n = (bytes + C - 1) / C;
+    for (size_t i = 0; i < n; ++i) {
+        const size_t off = i * C, len = bytes - off < C ? bytes - off : C;
+        if (i >= (size_t)K) CFEM_CUDA(p, cudaEventSynchronize(p->bev[i % K]));   // slot drained
+        p->pool->copy(p->bounce[i % K], (const char*)src + off, len);
+        CFEM_CUDA(p, cudaMemcpyAsync((char*)dev_dst + off, p->bounce[i % K], len,
+                                     cudaMemcpyHostToDevice, p->stream));
+        CFEM_CUDA(p, cudaEventRecord(p->bev[i % K], p->stream));
+    }
+    // the bounce buffers are reused by the next staged transfer: drain them
+    for (int k = 0; k < K && (size_t)k < n; ++k) CFEM_CUDA(p, cudaEventSynchronize(p->bev[k]));
+    p->staged_bytes += (long long)bytes;
+    return CFEM_OK;
+}
+
+// Host <-> device copy of a whole array: direct DMA for page-locked host
+// memory (asynchronous on the handle's stream), threaded staging for pageable
+// memory above 1 MiB (small arrays: the driver's own staging is as fast).
+static int copy_in(cfem_problem* p, void* dev_dst, const void* src, size_t bytes)
+{
+    if (bytes >= (size_t)(1 << 20) && !host_is_pinned(src)) return staged_h2d(p, dev_dst, src, bytes);
+    CFEM_CUDA(p, cudaMemcpyAsync(dev_dst, src, bytes, cudaMemcpyHostToDevice, p->stream));
+    return CFEM_OK;
+}
+
+static int copy_out(cfem_problem* p, void* dst, const void* dev_src, size_t bytes)
+{
+    if (bytes >= (size_t)(1 << 20) && !host_is_pinned(dst)) return staged_d2h(p, dst, dev_src, bytes);
+    CFEM_CUDA(p, cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToHost, p->stream));
+    return CFEM_OK;
+}
+
 }  // namespace cfem
 
 extern "C" {
@@ -209,6 +379,9 @@ void cfem_destroy(cfem_problem* p)
     if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
     cudaFree(p->k.reduce);
     cudaFree(p->flush_buf);
+    delete p->pool;
+    for (char* b : p->bounce) if (b) cudaFreeHost(b);
+    for (cudaEvent_t e : p->bev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : p->kev) if (e) cudaEventDestroy(e);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
@@ -247,9 +420,14 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     p->device = device;
     p->sm_count = sm_count;
     if (const char* w = getenv("CFEM_WAVES")) { p->waves = atoi(w) > 0 ? atoi(w) : 1; }
-    if (const char* w = getenv("CFEM_PREFETCH")) { p->prefetch = atoll(w); }
     if (const char* w = getenv("CFEM_PDL")) { p->use_pdl = atoi(w); }
     if (const char* w = getenv("CFEM_GRAPH")) { p->use_graph = atoi(w) != 0; }
+    if (const char* w = getenv("CFEM_COPY_THREADS")) { p->copy_threads = atoi(w) > 0 ? atoi(w) : 1; }
+    else {
+        const unsigned hw = std::thread::hardware_concurrency();
+        if (hw && (int)(hw / 2) < p->copy_threads) p->copy_threads = hw / 2 ? hw / 2 : 1;
+    }
+    if (const char* w = getenv("CFEM_COPY_CHUNK_MB")) { if (atoi(w) > 0) p->bounce_bytes = (size_t)atoi(w) << 20; }
     if (const char* w = getenv("CFEM_SKIP_PARAM")) { p->skip_param = atoi(w) != 0; }   // measurement only
     p->N = n_samples;
     p->batch = batch;
@@ -387,9 +565,7 @@ int cfem_set_dvec(cfem_problem* p, const double* dvec_host)
 {
     if (!p || !dvec_host) return CFEM_EINVAL;
     CFEM_CUDA(p, cudaSetDevice(p->device));
-    CFEM_CUDA(p, cudaMemcpyAsync(p->d_dvec, dvec_host,
-                                 (size_t)p->batch * p->k.ndec * sizeof(double),
-                                 cudaMemcpyHostToDevice, p->stream));
+    { int rc = cfem::copy_in(p, p->d_dvec, dvec_host, (size_t)p->batch * p->k.ndec * sizeof(double)); if (rc) return rc; }
     p->k.dvec = p->d_dvec;
     p->have_dvec = true;
     p->valid = 0;
@@ -409,10 +585,10 @@ int cfem_set_multipliers(cfem_problem* p, double obj_factor, const double* lambd
 {
     if (!p || (!lambda_host && p->k.ncons > 0)) return CFEM_EINVAL;
     CFEM_CUDA(p, cudaSetDevice(p->device));
-    if (p->k.ncons > 0)
-        CFEM_CUDA(p, cudaMemcpyAsync(p->d_lam, lambda_host,
-                                     (size_t)p->batch * p->k.ncons * sizeof(double),
-                                     cudaMemcpyHostToDevice, p->stream));
+    if (p->k.ncons > 0) {
+        int rc = cfem::copy_in(p, p->d_lam, lambda_host, (size_t)p->batch * p->k.ncons * sizeof(double));
+        if (rc) return rc;
+    }
     p->k.lam = p->d_lam;
     p->k.obj_factor = obj_factor;
     p->have_lam = true;
@@ -445,7 +621,7 @@ static int cfem_launch_graph(cfem_problem* p, unsigned mask, bool params)
     cfem::KArgs a1 = p->k;
     dim3 grid;
     size_t smem = 0;
-    gen::prepare_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, a1, grid, smem);
+    gen::prepare_sample(mask, p->batch, p->sm_count, p->waves, a1, grid, smem);
     if (g.exec && g.params != params) {         // CFEM_SKIP_PARAM toggled: rebuild
         cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph);
         g = cfem_problem::StepGraph();
@@ -460,7 +636,7 @@ static int cfem_launch_graph(cfem_problem* p, unsigned mask, bool params)
             if (e == cudaSuccess) e = cudaEventRecord(p->ev_join, p->aux_stream);
         }
         if (e == cudaSuccess)
-            e = gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, false, p->stream, p->k);
+            e = gen::launch_sample(mask, p->batch, p->sm_count, p->waves, false, p->stream, p->k);
         if (e == cudaSuccess && params) e = cudaStreamWaitEvent(p->stream, p->ev_join, 0);
         cudaGraph_t graph = nullptr;
         cudaError_t e2 = cudaStreamEndCapture(p->stream, &graph);
@@ -546,7 +722,7 @@ int cfem_eval(cfem_problem* p, uint32_t what)
         // the native trajectory lengths, where one evaluation is 15-40 us, the
         // two launches start about 1 us earlier from two streams (fork/join).
         CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->stream, p->k));
-        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, true, p->stream, p->k));
+        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, true, p->stream, p->k));
     } else {
         if (params) {
             CFEM_CUDA(p, cudaEventRecord(p->ev_fork, p->stream));
@@ -555,7 +731,7 @@ int cfem_eval(cfem_problem* p, uint32_t what)
             CFEM_CUDA(p, cudaEventRecord(p->ev_join, p->aux_stream));
         }
         if (p->timing) CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot], p->stream));
-        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->prefetch, false, p->stream, p->k));
+        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, false, p->stream, p->k));
         if (p->timing) {
             CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot + 1], p->stream));
             p->kev_count += 1;
@@ -607,9 +783,7 @@ int cfem_fetch_async(cfem_problem* p, uint32_t which, double* host_out)
         return cfem::fail(p, CFEM_ESTATE, "cfem_fetch: result not evaluated", cudaSuccess);
     CFEM_CUDA(p, cudaSetDevice(p->device));
     if (which & (CFEM_F | CFEM_GRAD)) { int rc = cfem_join_collect(p); if (rc) return rc; }
-    if (n)
-        CFEM_CUDA(p, cudaMemcpyAsync(host_out, src, n * sizeof(double),
-                                     cudaMemcpyDeviceToHost, p->stream));
+    if (n) { int rc = cfem::copy_out(p, host_out, src, n * sizeof(double)); if (rc) return rc; }
     return CFEM_OK;
 }
 
@@ -928,6 +1102,19 @@ int cfem_host_register(void* ptr, size_t bytes)
         return CFEM_ECUDA;
     }
     return CFEM_OK;
+}
+
+/* Ordered publication of control words in host memory shared between the
+ * solver process and the ranks (sharding.SharedVectors): a plain store / load
+ * is only ordered on x86. */
+void cfem_store_release_i64(int64_t* ptr, int64_t value)
+{
+    __atomic_store_n(ptr, value, __ATOMIC_RELEASE);
+}
+
+int64_t cfem_load_acquire_i64(const int64_t* ptr)
+{
+    return __atomic_load_n(ptr, __ATOMIC_ACQUIRE);
 }
 
 int cfem_host_unregister(void* ptr)

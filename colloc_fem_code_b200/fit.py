@@ -247,7 +247,7 @@ class BatchFitter:
             s.set_scaling(*per(i, scaling))
             solvers.append(s)
             steps.append(s.solve_steps(dec0s[i]))
-        sigma = solvers[0].obj_scale
+        sigma = _common_obj_scale([s.obj_scale for s in solvers])
         requests = [next(g) for g in steps]
         results = [None] * B
         active = set(range(B))
@@ -305,6 +305,18 @@ class BatchFitter:
     def close(self):
         self.buf.close()
         self.handle.close()
+
+
+def _common_obj_scale(scales):
+    """The batched kernel takes ONE obj_factor per launch (a kernel argument,
+    like IPOPT's eval_h): every problem of a batch must use the same
+    ``obj_scale``."""
+    scales = [float(v) for v in scales]
+    if any(v != scales[0] for v in scales[1:]):
+        raise ValueError('all problems of a batch must share obj_scale (the '
+                         'batched launch has a single obj_factor); got '
+                         f'{sorted(set(scales))}')
+    return scales[0]
 
 
 class _StructureOnly:
@@ -417,6 +429,20 @@ class ParallelBatchFitter:
 
     def _worker(self, mine, dec0s, dec_bounds, constr_bounds, scaling, tol,
                 max_iter):
+        import threading
+        import traceback
+        try:
+            self._worker_body(mine, dec0s, dec_bounds, constr_bounds, scaling,
+                              tol, max_iter)
+        except threading.BrokenBarrierError:
+            self.results.put(('error', f'worker {mine[:1]}: barrier broken '
+                              'by another process'))
+        except BaseException:       # noqa: BLE001 -- must not leave the others waiting
+            self.barrier.abort()
+            self.results.put(('error', traceback.format_exc()))
+
+    def _worker_body(self, mine, dec0s, dec_bounds, constr_bounds, scaling,
+                     tol, max_iter):
         from . import nlp
         try:                        # one BLAS thread per worker process
             import threadpoolctl
@@ -424,6 +450,7 @@ class ParallelBatchFitter:
         except Exception:
             pass
         sh, kind = self.sh, self.kind
+        wait = lambda: self.barrier.wait(self.BARRIER_TIMEOUT_S)  # noqa: E731
         steps, requests, active = {}, {}, set(mine)
 
         def per(i, arg):
@@ -450,8 +477,8 @@ class ParallelBatchFitter:
                         kind[i] = 1
                 else:
                     kind[i] = 0
-            self.barrier.wait()         # requests are posted
-            self.barrier.wait()         # results are in shared memory
+            wait()                      # requests are posted
+            wait()                      # results are in shared memory
             if kind[0] < 0:             # parent: everybody is done
                 break
             for i in list(active):
@@ -468,10 +495,16 @@ class ParallelBatchFitter:
                     done.append((i, x, {k: v for k, v in info.items()
                                         if not isinstance(v, np.ndarray)}))
                     active.discard(i)
-        self.results.put(done)
+        self.results.put(('done', done))
+
+    #: a round is one batched launch (parent) or one interior-point iteration
+    #: of a worker's slice; a side that does not show up within this time has
+    #: died or hung
+    BARRIER_TIMEOUT_S = 900.0
 
     def fit(self, dec0s, dec_bounds, constr_bounds, scaling, tol=1e-8,
             max_iter=300):
+        import threading
         import time
         backend = self._backend
         B, W = self.B, self.workers
@@ -483,26 +516,36 @@ class ParallelBatchFitter:
         for pr in procs:            # fork BEFORE this process touches CUDA
             pr.start()
         st = self._st
-        lib = backend.Library.for_structure(st)
-        data = [np.stack([np.ascontiguousarray(
-            p.structure.data[i]['source'], dtype=float)
-            for p in self.problems]) for i in range(len(st.data))]
-        h = backend.Handle(lib, st.N, data, st.scalar_values, batch=B,
-                           device=self.device)
+        try:
+            lib = backend.Library.for_structure(st)
+            data = [np.stack([np.ascontiguousarray(
+                p.structure.data[i]['source'], dtype=float)
+                for p in self.problems]) for i in range(len(st.data))]
+            h = backend.Handle(lib, st.N, data, st.scalar_values, batch=B,
+                               device=self.device)
+        except BaseException:
+            self.barrier.abort()        # the workers wait at the barrier
+            for pr in procs:
+                pr.join(30)
+            raise
         registered = []
         for name, arr in self.sh.items():
             if lib.cfem_host_register(arr.ctypes.data, arr.nbytes) == 0:
                 registered.append(arr)
-        sigma = scaling[0][0] if isinstance(scaling, list) else scaling[0]
         flat = {k: v.reshape(-1) for k, v in self.sh.items()}
         flat['lam'][:] = 0.0
+        wait = lambda: self.barrier.wait(self.BARRIER_TIMEOUT_S)  # noqa: E731
+        failure = None
         try:
+            sigma = _common_obj_scale(
+                [sc[0] for sc in scaling] if isinstance(scaling, list)
+                else [scaling[0]])
             while True:
-                self.barrier.wait()
+                wait()
                 kinds = self.kind.copy()
                 if not kinds.any():
                     self.kind[0] = -1
-                    self.barrier.wait()
+                    wait()
                     break
                 t0 = time.perf_counter()
                 h.set_dvec(flat['dvec'])
@@ -520,15 +563,35 @@ class ParallelBatchFitter:
                 h.synchronize()
                 self.seconds_gpu += time.perf_counter() - t0
                 self.launches += 1
-                self.barrier.wait()
+                wait()
+        except threading.BrokenBarrierError:
+            failure = 'a worker process failed or timed out'
+        except BaseException:
+            self.barrier.abort()        # release the workers, then re-raise
+            raise
         finally:
             for arr in registered:
                 lib.cfem_host_unregister(arr.ctypes.data)
             h.close()
         out = [None] * B
+        errors = []
+        import queue
         for _ in procs:
-            for i, x, info in self.results.get(timeout=600):
+            try:
+                tag, payload = self.results.get(timeout=60 if failure else 600)
+            except queue.Empty:
+                errors.append('a worker did not report')
+                continue
+            if tag == 'error':
+                errors.append(payload)
+                continue
+            for i, x, info in payload:
                 out[i] = (x, info)
         for pr in procs:
             pr.join(60)
+            if pr.is_alive():
+                pr.kill()
+        if failure or errors:
+            raise RuntimeError('ParallelBatchFitter: ' + (failure or '')
+                               + '\n' + '\n'.join(errors))
         return out

@@ -106,8 +106,16 @@ def problem_time_structure(p):
 class GpuEvaluator(Evaluator):
     """Callbacks served by the fused CUDA kernels of ``problem.backend``.
 
-    Inputs and results go through page-locked host buffers; ``new_x`` handling
-    (IPOPT passes it explicitly) avoids re-uploading an unchanged ``x``.
+    ``eval_fg`` / ``eval_all`` (the built-in driver's calls) return VIEWS into
+    one page-locked result block: they are valid until the next evaluation of
+    this object (the driver consumes them at once).  ``ipopt_eval`` (IPOPT's
+    five callbacks) moves the solver's own ``x`` / ``lambda`` / result arrays
+    with no intermediate NumPy copy: the C ABI DMAs page-locked arrays directly
+    and pipelines pageable ones through page-locked bounce buffers with a
+    threaded host copy (``cfem_set_dvec`` / ``cfem_fetch``, csrc/cfem_host.inl).
+    A solver whose buffers live as long as the problem can hand them to
+    :meth:`pin` once; ``new_x`` (IPOPT passes it explicitly) avoids
+    re-uploading an unchanged ``x``.
     """
 
     def __init__(self, problem):
@@ -116,8 +124,12 @@ class GpuEvaluator(Evaluator):
         self.h = self.be.handle
         self.n, self.m = problem.ndec, problem.ncons
         self.buf = backend.HostBuffers(self.h)
+        self._pinned = {}
         self.seconds = 0.0
         self.calls = 0
+        self.kernel_groups = 0
+        self._have_x = False
+        self._fresh = 0
 
     def jac_structure(self):
         return self.problem.constr_jac_ind()
@@ -128,33 +140,57 @@ class GpuEvaluator(Evaluator):
     def time_structure(self):
         return problem_time_structure(self.problem)
 
-    def _set_x(self, x):
-        self.buf.dvec[:] = x
-        self.buf.upload()
+    # -- explicit page-locking of solver-owned arrays ---------------------------
+    def pin(self, *arrays):
+        """Page-lock caller-owned arrays (``cfem_host_register``) so that the
+        DMA engines read / write them in place.  The caller guarantees that
+        each allocation stays alive and in place until :meth:`unpin` /
+        :meth:`close` -- never pin a buffer the solver may free or move."""
+        lib = self.h.lib
+        for arr in arrays:
+            ptr, nbytes = arr.ctypes.data, arr.nbytes
+            if nbytes == 0 or self._pinned.get(ptr, 0) >= nbytes:
+                continue
+            if ptr in self._pinned:
+                lib.cfem_host_unregister(ptr)
+                del self._pinned[ptr]
+            if lib.cfem_host_register(ptr, nbytes) != 0:
+                raise backend.CfemError('cfem_host_register failed for a '
+                                        f'{nbytes}-byte array')
+            self._pinned[ptr] = nbytes
+
+    def unpin(self, *arrays):
+        lib = self.h.lib
+        ptrs = [a.ctypes.data for a in arrays] if arrays \
+            else list(self._pinned)
+        for ptr in ptrs:
+            if ptr in self._pinned:
+                lib.cfem_host_unregister(ptr)
+                del self._pinned[ptr]
 
     def eval_fg(self, x):
         t0 = time.perf_counter()
-        self._set_x(x)
+        self.h.set_dvec(x)
+        self._have_x, self._fresh = True, 0
         self.h.eval(backend.F | backend.G)
         self.h.fetch_async(backend.F, self.buf.f)
         self.h.fetch_async(backend.G, self.buf.g)
         self.h.synchronize()
         self.seconds += time.perf_counter() - t0
         self.calls += 1
-        return float(self.buf.f[0]), self.buf.g.copy()
+        return float(self.buf.f[0]), self.buf.g
 
     def eval_all(self, x, sigma, lam):
         t0 = time.perf_counter()
-        self.buf.dvec[:] = x
-        self.buf.lam[:] = lam
-        self.buf.upload(sigma)          # one H2D copy: [x | lambda]
+        self.h.set_dvec(x)
+        self.h.set_multipliers(sigma, lam)
+        self._have_x, self._fresh = True, 0
         self.h.eval(backend.ALL)
         self.buf.fetch_all()            # one D2H copy: [f | grad | g | jac | hess]
         self.seconds += time.perf_counter() - t0
         self.calls += 1
         b = self.buf
-        return (float(b.f[0]), b.grad.copy(), b.g.copy(), b.jac.copy(),
-                b.hess.copy())
+        return float(b.f[0]), b.grad, b.g, b.jac, b.hess
 
     # IPOPT-shaped single callbacks (used by IpoptSolver).  IPOPT asks for f
     # and g at every trial point and for grad f, the Jacobian and the Hessian
@@ -170,25 +206,28 @@ class GpuEvaluator(Evaluator):
               backend.HESS: backend.HESS}
 
     def ipopt_eval(self, which, x, new_x, out, sigma=None, lam=None):
+        """One IPOPT callback: result ``which`` at ``x`` into the solver-owned
+        array ``out`` (``sigma`` / ``lam`` for the Hessian)."""
         t0 = time.perf_counter()
-        if new_x or not getattr(self, '_have_x', False):
-            self._set_x(x)
+        h = self.h
+        if new_x or not self._have_x:
+            h.set_dvec(x)               # from the solver's own x
             self._have_x = True
             self._fresh = 0
         if which == backend.HESS:
-            self.buf.lam[:] = lam
-            self.h.set_multipliers(sigma, self.buf.lam)
+            h.set_multipliers(sigma, lam)
             self._fresh &= ~backend.HESS
         if not (self._fresh & which):
             mask = self._GROUP[which]
-            self.h.eval(mask)
+            h.eval(mask)
             self._fresh |= mask
-            self.kernel_groups = getattr(self, 'kernel_groups', 0) + 1
-        self.h.fetch(which, out)
+            self.kernel_groups += 1
+        h.fetch(which, out)             # into the solver's own array
         self.seconds += time.perf_counter() - t0
         self.calls += 1
 
     def close(self):
+        self.unpin()
         self.buf.close()
 
 
@@ -958,8 +997,15 @@ class IpoptSolver(Solver):
 
     ``x``, ``g``, ``grad_f`` and ``values`` are IPOPT-owned host buffers, valid
     only during a callback; results are copied straight into them
-    (``cfem_fetch``).  A CUDA failure is reported to IPOPT as an evaluation
-    error (callback returns FALSE).
+    (``cfem_fetch``: pageable arrays are pipelined through page-locked bounce
+    buffers by a threaded copy, no assumption on the pointers).  IPOPT's
+    ``TNLPAdapter`` allocates ``x``, ``g``, ``grad_f`` and the Jacobian values
+    once per problem; ``pin_buffers`` (``CFEM_PIN_IPOPT_BUFFERS=1``, off by
+    default) page-locks those on first sight so that they are DMA targets
+    themselves -- only for IPOPT builds known to keep them in place; the
+    Hessian values array (a fresh matrix per iterate) is never pinned.  A CUDA
+    failure is reported to IPOPT as an evaluation error (callback returns
+    FALSE).
     """
 
     name = 'ipopt'
@@ -992,7 +1038,18 @@ class IpoptSolver(Solver):
         jr, jc = ev.jac_structure()
         hr, hc = ev.hess_structure()
         if max(len(jr), len(hr), n, m) >= 2 ** 31:
-            raise OverflowError('IPOPT Index is a 32-bit int')
+            raise OverflowError(
+                "IPOPT's Index is a 32-bit int: n, m, nnz_jac and nnz_hess "
+                f'must stay below 2**31 (got n={n}, m={m}, nnz_jac={len(jr)}, '
+                f'nnz_hess={len(hr)}); shorten the trajectory or build IPOPT '
+                'with 64-bit indices')
+        self.pin_buffers = os.environ.get('CFEM_PIN_IPOPT_BUFFERS') == '1'
+        pin = getattr(ev, 'pin', None)
+
+        def stable(*arrays):
+            if self.pin_buffers and pin is not None:
+                pin(*arrays)
+            return arrays
         self._jr, self._jc = jr.astype(np.int32), jc.astype(np.int32)
         self._hr, self._hc = hr.astype(np.int32), hc.astype(np.int32)
 
@@ -1017,11 +1074,13 @@ class IpoptSolver(Solver):
 
         @guard
         def eval_grad_f(n_, x, new_x, grad, _):
-            ev.ipopt_eval(backend.GRAD, arr(x, n), new_x, arr(grad, n))
+            ev.ipopt_eval(backend.GRAD, *stable(arr(x, n)), new_x,
+                          *stable(arr(grad, n)))
 
         @guard
         def eval_g(n_, x, new_x, m_, g, _):
-            ev.ipopt_eval(backend.G, arr(x, n), new_x, arr(g, m))
+            ev.ipopt_eval(backend.G, *stable(arr(x, n)), new_x,
+                          *stable(arr(g, m)))
 
         @guard
         def eval_jac_g(n_, x, new_x, m_, nele, irow, jcol, values, _):
@@ -1029,8 +1088,8 @@ class IpoptSolver(Solver):
                 arr(irow, nele)[:] = self._jr
                 arr(jcol, nele)[:] = self._jc
             else:
-                ev.ipopt_eval(backend.JAC, arr(x, n), new_x,
-                              arr(values, nele))
+                ev.ipopt_eval(backend.JAC, *stable(arr(x, n)), new_x,
+                              *stable(arr(values, nele)))
 
         @guard
         def eval_h(n_, x, new_x, sigma, m_, lam, new_lam, nele, irow, jcol,
@@ -1078,10 +1137,16 @@ class IpoptSolver(Solver):
         mult_g, mult_L, mult_U = np.zeros(m), np.zeros(n), np.zeros(n)
         t0 = time.perf_counter()
         ev_t0 = getattr(self.ev, 'seconds', 0.0)
-        status = lib.IpoptSolve(
-            nlp, x.ctypes.data_as(_dp), g.ctypes.data_as(_dp),
-            ctypes.cast(ctypes.byref(obj), _dp), mult_g.ctypes.data_as(_dp),
-            mult_L.ctypes.data_as(_dp), mult_U.ctypes.data_as(_dp), None)
+        try:
+            status = lib.IpoptSolve(
+                nlp, x.ctypes.data_as(_dp), g.ctypes.data_as(_dp),
+                ctypes.cast(ctypes.byref(obj), _dp),
+                mult_g.ctypes.data_as(_dp), mult_L.ctypes.data_as(_dp),
+                mult_U.ctypes.data_as(_dp), None)
+        finally:
+            unpin = getattr(self.ev, 'unpin', None)
+            if self.pin_buffers and unpin is not None:
+                unpin()         # IPOPT's arrays do not outlive the solve
         total = time.perf_counter() - t0
         cb = getattr(self.ev, 'seconds', 0.0) - ev_t0
         info = {'status': int(status), 'solver': self.name, 'obj': obj.value,

@@ -222,6 +222,22 @@ class ShardedEvaluator:
             raise backend.CfemError(f'shard layout mismatch: {got} vs {want}')
         self.n_reduce = len(self.lib.model['reduce'])
 
+    def prepare_peer_reduce(self, group=None):
+        """Rank-local half of :meth:`enable_peer_reduce`: allocate and zero the
+        symmetric inbox.  No collective is issued, so a failure here (no
+        symmetric memory, no P2P) can be voted on before any rank enters the
+        rendezvous (:func:`agree_on_peer_reduce`)."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = group or dist.group.WORLD
+        world = dist.get_world_size(group)
+        n_inbox, n_flag = self.handle.peer_layout(world)
+        buf = symm.empty(n_inbox + n_flag, dtype=torch.float64,
+                         device=torch.device('cuda', torch.cuda.current_device()))
+        buf.zero_()
+        self._peer_buf = (buf, n_inbox)
+
     def enable_peer_reduce(self, group=None, pipelined=False):
         """Switch from ``all_reduce`` + ``cfem_apply_reduced`` to the fused
         in-kernel exchange over NVLink peer memory (``cfem_set_peers``).
@@ -238,10 +254,9 @@ class ShardedEvaluator:
         import torch.distributed._symmetric_memory as symm
         group = group or dist.group.WORLD
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        n_inbox, n_flag = self.handle.peer_layout(world)
-        buf = symm.empty(n_inbox + n_flag, dtype=torch.float64,
-                         device=torch.device('cuda', torch.cuda.current_device()))
-        buf.zero_()
+        if getattr(self, '_peer_buf', None) is None:
+            self.prepare_peer_reduce(group)
+        buf, n_inbox = self._peer_buf
         hdl = symm.rendezvous(buf, group)
         ptrs = [int(p) for p in hdl.buffer_ptrs]
         ptrs[rank] = buf.data_ptr()     # own inbox: the local mapping
@@ -251,6 +266,29 @@ class ShardedEvaluator:
                               [p + 8 * n_inbox for p in ptrs])
         self.handle.set_peer_mode(pipelined)
         self._peer = (buf, hdl)         # keep the mapping alive
+        return True
+
+    def agree_on_peer_reduce(self, group=None, pipelined=False):
+        """Collective: every rank tries the rank-local preparation, the ranks
+        vote, and only if ALL succeeded do they enter the rendezvous -- the
+        sequence of collectives is the same on every rank whatever fails
+        where.  Returns True if the fused exchange is on."""
+        import torch
+        import torch.distributed as dist
+        try:
+            self.prepare_peer_reduce(group)
+            ok = 1
+        except Exception:
+            self._peer_buf = None
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32,
+                            device=torch.device('cuda',
+                                                torch.cuda.current_device()))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self._peer_buf = None
+            return False
+        self.enable_peer_reduce(group, pipelined)
         return True
 
     def set_point(self, dvec, obj_factor, lam):
@@ -436,6 +474,7 @@ class SolverFacingEvaluator:
                     continue            # replicated parameters: whoever is first
                 vec[g0:g0 + n] = 0.0
         barrier()
+        self._lib = lib
         self.pinned = self.sv.page_lock(lib) if lib is not None else False
         self._seq = 0
         self._have_x = False
@@ -462,6 +501,28 @@ class SolverFacingEvaluator:
         h.synchronize()
 
     TIMEOUT_S = 600.0       # a rank that died must not hang the others
+    #: ranks > 0 wait for the solver between callbacks (its KKT factorisation
+    #: can take long), but not for ever: rank 0 may have died without STOP
+    SERVE_TIMEOUT_S = float(os.environ.get('CFEM_SERVE_TIMEOUT_S', 6 * 3600))
+
+    def _publish(self, index, value):
+        """Store a control word AFTER everything written before it (vectors,
+        request, obj_factor): release store through the C ABI where the
+        library provides it (needed on weakly ordered hosts, e.g. aarch64);
+        a plain store is enough on x86."""
+        store = getattr(self._lib, 'cfem_store_release_i64', None) \
+            if self._lib is not None else None
+        if store is not None:
+            store(self.sv.ctrl.ctypes.data + 8 * index, int(value))
+        else:
+            self.sv.ctrl[index] = value
+
+    def _observe(self, index):
+        load = getattr(self._lib, 'cfem_load_acquire_i64', None) \
+            if self._lib is not None else None
+        if load is not None:
+            return int(load(self.sv.ctrl.ctypes.data + 8 * index))
+        return int(self.sv.ctrl[index])
 
     @classmethod
     def _wait(cls, cond, timeout=None):
@@ -480,26 +541,27 @@ class SolverFacingEvaluator:
         ctrl = self.sv.ctrl
         seq = 0
         while True:
-            self._wait(lambda: ctrl[0] != seq)
-            seq = int(ctrl[0])
+            self._wait(lambda: self._observe(0) != seq, self.SERVE_TIMEOUT_S)
+            seq = self._observe(0)
             request = int(ctrl[1])
             if request == SharedVectors.STOP:
-                ctrl[SharedVectors._CTRL + self.rank] = seq
+                self._publish(SharedVectors._CTRL + self.rank, seq)
                 return
             self._execute(request)
-            ctrl[SharedVectors._CTRL + self.rank] = seq
+            self._publish(SharedVectors._CTRL + self.rank, seq)
 
     def _request(self, request):
         """Rank 0: post, do the own share, wait for everybody."""
         ctrl = self.sv.ctrl
         self._seq += 1
         ctrl[1] = request
-        ctrl[0] = self._seq             # published last (x86 store order)
+        self._publish(0, self._seq)     # published last, with release order
         if request != SharedVectors.STOP:
             self._execute(request)
-        ctrl[SharedVectors._CTRL] = self._seq
-        done = ctrl[SharedVectors._CTRL:SharedVectors._CTRL + self.world]
-        self._wait(lambda: (done == self._seq).all(), self.TIMEOUT_S)
+        self._publish(SharedVectors._CTRL, self._seq)
+        base = SharedVectors._CTRL
+        self._wait(lambda: all(self._observe(base + r) == self._seq
+                               for r in range(self.world)), self.TIMEOUT_S)
 
     def stop(self):
         if self.rank == 0 and self._seq >= 0:
@@ -584,17 +646,8 @@ def solver_facing_evaluator(problem, rank, world, device=0, group=None,
     hook = None
     if world > 1:
         mode = reduce
-        if mode == 'peer':
-            try:
-                ev.enable_peer_reduce(group)
-            except Exception:
-                mode = 'nccl'
-            ok = torch.tensor([mode == 'peer'], dtype=torch.int32,
-                              device=f'cuda:{device}')
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-            if mode == 'peer' and int(ok.item()) == 0:
-                ev.handle.set_peers(0, 1, [], [])
-                mode = 'nccl'
+        if mode == 'peer' and not ev.agree_on_peer_reduce(group):
+            mode = 'nccl'
         if mode != 'peer':
             ptr = ev.handle.device_ptrs()['reduce']
 

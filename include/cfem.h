@@ -226,10 +226,22 @@ int64_t      cfem_launch_count(const cfem_problem* p);
 int          cfem_flush_l2(cfem_problem* p, size_t bytes);
 
 /* ---- pinned host memory for the IPOPT-facing buffers ----------------------- */
+/* Host arrays passed to cfem_set_dvec / cfem_set_multipliers / cfem_fetch* may
+ * be ordinary pageable memory (the arrays IPOPT owns, IpStdCInterface.h:
+ * Eval_F_CB .. Eval_H_CB): arrays above 1 MiB are then pipelined through
+ * page-locked bounce buffers with a multi-threaded host copy
+ * (CFEM_COPY_THREADS, CFEM_COPY_CHUNK_MB) and the call returns when the data
+ * has arrived.  Page-locked arrays (cfem_host_alloc, or cfem_host_register of
+ * an allocation the caller keeps in place) are DMA sources / targets
+ * themselves; such copies are asynchronous on the handle's stream. */
 void*        cfem_host_alloc(size_t bytes);
 void         cfem_host_free(void* ptr);
 int          cfem_host_register(void* ptr, size_t bytes);
 int          cfem_host_unregister(void* ptr);
+/* Release store / acquire load of a control word in host memory shared by the
+ * solver process and the ranks of a time-sharded problem (no CUDA involved). */
+void         cfem_store_release_i64(int64_t* ptr, int64_t value);
+int64_t      cfem_load_acquire_i64(const int64_t* ptr);
 
 #ifdef __cplusplus
 }

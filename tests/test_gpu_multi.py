@@ -1,6 +1,8 @@
-"""Two-GPU run of the time-sharded evaluation (skipped with fewer GPUs):
-results assembled from two ranks -- with the fused in-kernel peer-memory
-reduction and with NCCL all_reduce -- equal the single-GPU evaluation."""
+"""Multi-GPU runs of the time-sharded evaluation at world = 2, 4 and 8 (each
+skipped with fewer GPUs): results assembled from all ranks -- with the fused
+in-kernel peer-memory reduction (synchronous and pipelined) and with NCCL
+all_reduce -- equal the single-GPU evaluation, and every rank holds the same
+bits of the reduced objective / parameter gradient."""
 
 import os
 import socket
@@ -63,6 +65,12 @@ def _rank_main(rank, world, port, mode, out):
                                      np.zeros(ev.shard.global_size(k)))
                  for k in ('grad', 'g', 'jac', 'hess')}
         parts['f'] = float(res['f'][0])
+        # the reduced parameter block of the gradient, as this rank holds it
+        slots = ev.lib.model['reduce'][1:]
+        st = p.structure
+        loc_off = dict(zip(st.var_names, h.layout()['var_offset']))
+        parts['red'] = np.array([res['grad'][loc_off[st.var_names[v]] + fl]
+                                 for v, fl in slots])
         gathered = [None] * world
         dist.gather_object(parts, gathered if rank == 0 else None, dst=0)
         if rank == 0:
@@ -70,7 +78,10 @@ def _rank_main(rank, world, port, mode, out):
             ref = {'f': p.obj(d), 'grad': p.obj_grad(d), 'g': p.constr(d),
                    'jac': p.constr_jac_val(d),
                    'hess': p.lag_hess_val(d, sigma, lam)}
-            assert gathered[0]['f'] == gathered[1]['f']     # same bits
+            for other in gathered[1:]:                      # same bits
+                assert gathered[0]['f'] == other['f']
+                np.testing.assert_array_equal(other['red'],
+                                              gathered[0]['red'])
             np.testing.assert_allclose(gathered[0]['f'], ref['f'], rtol=1e-13)
             for k in ('g', 'jac', 'hess'):
                 full = sum(g[k] for g in gathered)
@@ -86,17 +97,18 @@ def _rank_main(rank, world, port, mode, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('world', [2, 4, 8])
 @pytest.mark.parametrize('mode', ['peer', 'peer_pipelined', 'nccl'])
-def test_two_gpu_sharded_equals_single(mode):
+def test_multi_gpu_sharded_equals_single(mode, world):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs two GPUs')
+    if torch.cuda.device_count() < world:
+        pytest.skip(f'needs {world} GPUs')
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, mode, out))
-             for r in range(2)]
+    procs = [ctx.Process(target=_rank_main, args=(r, world, port, mode, out))
+             for r in range(world)]
     for pr in procs:
         pr.start()
     for pr in procs:
@@ -164,17 +176,19 @@ def _solver_rank_main(rank, world, port, mode, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('mode', ['peer', 'nccl'])
-def test_two_gpu_one_solver_process(mode):
+@pytest.mark.parametrize('mode,world', [('peer', 2), ('nccl', 2), ('peer', 4),
+                                        ('peer', 8)])
+def test_multi_gpu_one_solver_process(mode, world):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs two GPUs')
+    if torch.cuda.device_count() < world:
+        pytest.skip(f'needs {world} GPUs')
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     out = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_solver_rank_main,
-                         args=(r, 2, port, mode, out)) for r in range(2)]
+                         args=(r, world, port, mode, out))
+             for r in range(world)]
     for pr in procs:
         pr.start()
     for pr in procs:

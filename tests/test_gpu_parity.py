@@ -14,25 +14,10 @@ from oracle import ref_models
 
 pytestmark = pytest.mark.gpu
 
-RTOL = 1e-12
+from parity_helpers import RTOL, check_against, exact_masks
+from parity_helpers import scale_of as _scale
+
 MASKS = (1, 3, 4, 8, 16, 5, 15, 31)
-
-
-def _scale(*arrays):
-    return max(1.0, *(float(np.max(np.abs(a))) for a in arrays if a.size))
-
-
-def check_against(res, ref, scale):
-    """res / ref: dicts with f, grad, g, jac, hess."""
-    np.testing.assert_allclose(res['f'], ref['f'], rtol=RTOL)
-    np.testing.assert_allclose(res['grad'], ref['grad'], rtol=RTOL,
-                               atol=1e-300)
-    np.testing.assert_allclose(res['g'], ref['g'], rtol=RTOL,
-                               atol=RTOL * scale)
-    np.testing.assert_allclose(res['jac'], ref['jac'], rtol=RTOL,
-                               atol=RTOL * scale)
-    np.testing.assert_allclose(res['hess'], ref['hess'], rtol=RTOL,
-                               atol=RTOL * scale)
 
 
 def cuda_callbacks(p, dvec, sigma, lam):
@@ -55,13 +40,14 @@ def test_golden_fixtures(golden):
     ref = {'f': g['f'], 'grad': g['grad'], 'g': g['g'], 'jac': g['jac_val'],
            'hess': g['hess_val']}
     scale = _scale(g['dvec'], g['y'], g['u']) ** 2 * (nx + nu + ny + 1)
+    exact = exact_masks(p)
     check_against(cuda_callbacks(p, g['dvec'], g['obj_factor'], g['lam']),
-                  ref, scale)
+                  ref, scale, exact)
     # fused single pass
     f, grad, gg, jac, hess = p.backend.eval_all(g['dvec'], g['obj_factor'],
                                                 g['lam'])
     check_against({'f': f, 'grad': grad, 'g': gg, 'jac': jac, 'hess': hess},
-                  ref, scale)
+                  ref, scale, exact)
 
 
 def test_every_kernel_variant(golden):
@@ -98,6 +84,10 @@ CASES = [
     # extension without reference counterpart: trapezoidal collocation
     ('trapezoid', (2, 1, 2), 2), ('trapezoid', (2, 1, 2), 1000),
     ('trapezoid', (3, 2, 2), 4097),
+    # BASELINE sizes: the exact bench.py workload (attas_sp_ml at N = 1e6) and
+    # the other two script shapes, entry for entry against the oracle
+    ('ml', (2, 1, 2), 1_000_000), ('balanced', (5, 3, 3), 1_000_000),
+    ('ndisc_zoh', (4, 2, 7), 1_000_000),
 ]
 
 
@@ -113,7 +103,25 @@ def test_random_point_vs_oracle(kind, dims, N):
     sigma = 0.8
     scale = _scale(dvec, exp['y'], exp['u']) ** 2 * (nx + nu + ny + 1)
     check_against(cuda_callbacks(p, dvec, sigma, lam),
-                  oracle_callbacks(o, dvec, sigma, lam), scale)
+                  oracle_callbacks(o, dvec, sigma, lam), scale,
+                  exact_masks(p))
+
+
+def test_bench_workload_vs_oracle():
+    """bench.py's own inputs (same family, dims, seed, N and evaluation point
+    as the timed run), fused single pass, against the oracle."""
+    import bench
+    nx, nu, ny = bench.DIMS
+    N = bench.N_PER_GPU
+    exp = synthetic.experiment(0, N, nx, nu, ny)
+    p = families.make_problem(bench.KIND, exp['y'], exp['u'], nx)
+    o = ref_models.make_problem(bench.KIND, exp['y'], exp['u'], nx)
+    dvec, lam, sigma = synthetic.evaluation_point(p, exp)
+    f, grad, g, jac, hess = p.backend.eval_all(dvec, sigma, lam)
+    scale = _scale(dvec, exp['y'], exp['u']) ** 2 * (nx + nu + ny + 1)
+    check_against({'f': f, 'grad': grad, 'g': g, 'jac': jac, 'hess': hess},
+                  oracle_callbacks(o, dvec, sigma, lam), scale,
+                  exact_masks(p))
 
 
 def test_known_answer_noise_free():

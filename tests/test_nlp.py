@@ -179,3 +179,38 @@ def test_ipopt_binding_reports_evaluation_errors(fake_ipopt):
     s.close()
     assert info['status'] == -13
     assert 'device lost' in str(info['last_error'])
+
+
+def test_parallel_batch_fitter_does_not_hang_when_the_parent_fails():
+    """No CUDA device here: cfem_create fails in the parent after the workers
+    were forked.  The barrier must be aborted so that the workers exit and the
+    error surfaces (it used to block for ever)."""
+    import time
+    from colloc_fem_code_b200 import backend, families, fit, synthetic
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip('needs a box WITHOUT a CUDA device')
+    except ImportError:
+        pass
+    nx, nu, ny, N = 2, 1, 2, 40
+    problems = []
+    for s in range(2):
+        exp = synthetic.experiment(s, N, nx, nu, ny)
+        problems.append(families.make_problem('innovation', exp['y'],
+                                              exp['u'], nx))
+    p = problems[0]
+    pf = fit.ParallelBatchFitter(problems, workers=2)
+    bounds = np.repeat([[-np.inf], [np.inf]], p.ndec, axis=-1)
+    t0 = time.perf_counter()
+    with pytest.raises(backend.CfemError):
+        pf.fit([np.zeros(p.ndec)] * 2, bounds, np.zeros((2, p.ncons)),
+               (-1.0, None, None), max_iter=3)
+    assert time.perf_counter() - t0 < 60
+
+
+def test_batch_needs_one_obj_scale():
+    from colloc_fem_code_b200 import fit
+    assert fit._common_obj_scale([-1.0, -1.0]) == -1.0
+    with pytest.raises(ValueError):
+        fit._common_obj_scale([-1.0, 1.0])

@@ -26,6 +26,13 @@ if os.environ.get('SWEEP_SET', 'occupancy') == 'store':
         VARIANTS.append(dict(tile=128, pass_budget=6, store=st_))
         VARIANTS.append(dict(tile=128, pass_budget=6, store=st_,
                              experiment='noload'))
+elif os.environ.get('SWEEP_SET') == 'r2':
+    # round 2: balanced persistent schedule (waves = 1, 2) against one tile
+    # per CTA (waves = 8), tile size x launch bounds
+    for tile, mbs in ((128, (None, 7, 8)), (64, (None, 14, 16)),
+                      (256, (None, 3, 4))):
+        for mb in mbs:
+            VARIANTS.append(dict(tile=tile, pass_budget=6, min_blocks=mb))
 else:       # resident CTAs per SM: launch bounds x single staging buffer
     for tile, mbs in ((64, (None, 16, 18, 20)), (128, (None, 8, 9, 10)),
                       (256, (None, 4, 5))):
@@ -84,7 +91,8 @@ def run():
             h.eval(31)
             ms.append(h.last_sample_kernel_ms())
         ms = ms[3:]
-        rec = dict(v, waves=waves, single_buf=single, ms_min=min(ms), ms_med=float(np.median(ms)),
+        f_val = float(h.fetch(1)[0])        # sanity: the same objective everywhere
+        rec = dict(v, waves=waves, single_buf=single, ms_min=min(ms), ms_med=float(np.median(ms)), f=f_val,
                    gbs=balg * N / (np.median(ms) * 1e-3) / 1e9)
         print(json.dumps(rec), flush=True)
         out.append(rec)
