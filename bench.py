@@ -64,6 +64,37 @@ UNIT = 'callback sets/s (f+grad+g+Jac+Hess, N=1e6 samples per set)'
 FLUSH_BYTES = 256 << 20
 
 
+SCALING = 'weak'
+DEFAULT_WORKLOAD = True
+
+
+def configure_workload(args):
+    """Apply --kind / --dims / --n-per-gpu / --n-total to the module-level
+    workload description."""
+    global KIND, DIMS, N_PER_GPU, SCALING, UNIT, DEFAULT_WORKLOAD
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    kind, dims = args.kind, tuple(int(c) for c in args.dims)
+    n = args.n_per_gpu
+    if args.n_total:
+        if args.n_total % world:
+            raise SystemExit('--n-total must be a multiple of the GPU count')
+        n = args.n_total // world
+        SCALING = 'strong'
+        UNIT = ('callback sets/s (f+grad+g+Jac+Hess, '
+                f'N={args.n_total} samples per set)')
+    elif n != N_PER_GPU:
+        UNIT = f'callback sets/s (f+grad+g+Jac+Hess, N={n} samples per set)'
+    DEFAULT_WORKLOAD = (kind, dims, n, SCALING) == (KIND, DIMS, N_PER_GPU,
+                                                    'weak')
+    KIND, DIMS, N_PER_GPU = kind, dims, n
+
+
+SCRIPT_OF = {'ml': 'attas_sp_ml', 'balanced': 'attas_sp_innov_bal / '
+             'blackbox_innov_bal', 'ndisc_zoh': 'hfb320_sqrt_zoh / '
+             'attas_sp_ml_ndisc', 'ml_zoh': 'attas_sp_ml_zoh',
+             'innovation': 'attas_sp_innov', 'ml_balanced': 'mc_blackbox_cfem'}
+
+
 def algorithmic_bytes_per_sample(nx, nu, ny):
     """every input read once, every output written
     once, per sample, for the per-sample functions."""
@@ -247,7 +278,11 @@ def workload_config(world, reduce_mode='none'):
            'nccl': 'NCCL allreduce of objective + parameter gradient',
            'none': ''}[reduce_mode]
     return {
-        'workload': ('attas_sp_ml: MaximumLikelihoodDT (nx,nu,ny)=(2,1,2), '
+        'workload': (f'{SCRIPT_OF.get(KIND, KIND)}: family {KIND} '
+                     f'(nx,nu,ny)=({nx},{nu},{ny}), synthetic trajectory, '
+                     f'N={N_PER_GPU} samples per GPU'
+                     if not DEFAULT_WORKLOAD else
+                     'attas_sp_ml: MaximumLikelihoodDT (nx,nu,ny)=(2,1,2), '
                      f'synthetic trajectory, N={N_PER_GPU} samples per GPU'),
         'family': KIND, 'dims': list(DIMS),
         'n_samples_total': N_PER_GPU * world,
@@ -429,6 +464,83 @@ def run_ours(args, out):
     # ---- end to end through the host API (pinned host buffers) ---------------
     e2e_steps = 30              # >= 30: min and median are reported too
     e2e_step_s = []
+    e2e_ms, e2e_h2d, e2e_d2h, solver_api = 0.0, 0, 0, None
+    e2e_note = 'skipped (--no-e2e)'
+    if not args.no_e2e:
+        (e2e_ms, e2e_h2d, e2e_d2h, e2e_note, solver_api) = run_e2e(
+            args, torch, dist, backend, sharding, problem, ev, h, rank,
+            world, local_rank, reduce_mode, red, ptrs, dvec, lam, sigma,
+            ldvec, llam, e2e_steps, e2e_step_s, sync_all)
+    else:
+        e2e_step_s.append(0.0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        # weak: N_PER_GPU-sample callback sets; strong: whole-trajectory sets
+        sets = args.steps * (world if SCALING == 'weak' else 1)
+        e2e_sets = e2e_steps * (world if SCALING == 'weak' else 1)
+        value = sets / (total_ms * 1e-3)
+        balg = algorithmic_bytes_per_sample(nx, nu, ny)
+        kms = float(np.mean(kernel_ms))
+        peak, peak_kind = measured_peak()
+        achieved = balg * ev.shard.n_local / (kms * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': SCALING, 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': workload_config(world, reduce_mode),
+            'samples_per_s': value * N_PER_GPU
+            * (world if SCALING == 'strong' else 1),
+            'numa_node': numa_node, 'numa_note': numa_note,
+            'per_rank': per_rank,
+            'ms_per_step_with_kernel_events': sum(probe['step_ms'])
+            / args.steps,
+            'gpu_launches': int(launches),
+            'wall_s_timed_region': wall,
+            'host_enqueue_s': host_enqueue,
+            'clocks': clocks,
+            'e2e': {
+                'value': e2e_sets / (e2e_ms * 1e-3) if e2e_ms else None,
+                'unit': UNIT,
+                'h2d_bytes_per_step': e2e_h2d, 'd2h_bytes_per_step': e2e_d2h,
+                'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
+                'ms_per_step_min': 1e3 * min(e2e_step_s),
+                'ms_per_step_median': 1e3 * float(np.median(e2e_step_s)),
+                'note': e2e_note},
+            'reduce_check': reduce_check,
+            'roofline': {
+                'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+                'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': ncu_traffic(),
+                'kernel': 'cfem_sample_kernel_m31',
+                'kernel_ms': kms, 'algorithmic_bytes_per_sample': balg,
+                'samples_per_launch': ev.shard.n_local,
+                'peak_source': f'{peak_kind} (MEASURED_PEAKS.json hbm_gbs, '
+                               'burst copy)',
+                'frac_of_nominal_8TBs': achieved / 8000.0},
+        }
+        if sync_ms is not None:
+            line['value_sync'] = sets / (sync_ms * 1e-3)
+            line['ms_per_step_sync'] = sync_ms / args.steps
+        if solver_api is not None:
+            line['e2e_solver_api'] = solver_api['pageable']
+            line['e2e_solver_api_pinned'] = solver_api['pinned']
+        if world == 1 and not args.no_cpu_baseline and DEFAULT_WORKLOAD:
+            line['cpu_baseline'] = cpu_baseline()
+        out.emit(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    if not reduce_check['ok']:
+        raise SystemExit(f'reduce_check failed: {reduce_check}')
+
+
+def run_e2e(args, torch, dist, backend, sharding, problem, ev, h, rank, world,
+            local_rank, reduce_mode, red, ptrs, dvec, lam, sigma, ldvec, llam,
+            e2e_steps, e2e_step_s, sync_all):
+    """The end-to-end legs: host buffers -> H2D -> kernels -> D2H, every
+    step (see the module docstring)."""
     sfe = None
     if world > 1:
         # ONE solver-facing process (rank 0) in front of all shards: x, lambda
@@ -533,63 +645,7 @@ def run_ours(args, out):
                                        False, res, 2 + e2e_steps - 1),
             'pinned': solver_api_leg(problem, dvec, lam, sigma, e2e_steps,
                                      True, res, 2 + e2e_steps - 1)}
-    clocks = sampler.stop() if rank == 0 else None
-
-    if rank == 0:
-        sets = args.steps * world           # N=1e6-sample callback sets
-        value = sets / (total_ms * 1e-3)
-        balg = algorithmic_bytes_per_sample(nx, nu, ny)
-        kms = float(np.mean(kernel_ms))
-        peak, peak_kind = measured_peak()
-        achieved = balg * ev.shard.n_local / (kms * 1e-3) / 1e9
-        line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic',
-            'config': workload_config(world, reduce_mode),
-            'samples_per_s': value * N_PER_GPU,
-            'numa_node': numa_node, 'numa_note': numa_note,
-            'per_rank': per_rank,
-            'ms_per_step_with_kernel_events': sum(probe['step_ms'])
-            / args.steps,
-            'gpu_launches': int(launches),
-            'wall_s_timed_region': wall,
-            'host_enqueue_s': host_enqueue,
-            'clocks': clocks,
-            'e2e': {
-                'value': e2e_steps * world / (e2e_ms * 1e-3), 'unit': UNIT,
-                'h2d_bytes_per_step': e2e_h2d, 'd2h_bytes_per_step': e2e_d2h,
-                'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
-                'ms_per_step_min': 1e3 * min(e2e_step_s),
-                'ms_per_step_median': 1e3 * float(np.median(e2e_step_s)),
-                'note': e2e_note},
-            'reduce_check': reduce_check,
-            'roofline': {
-                'bound': 'hbm', 'achieved': achieved, 'peak': peak,
-                'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': ncu_traffic(),
-                'kernel': 'cfem_sample_kernel_m31',
-                'kernel_ms': kms, 'algorithmic_bytes_per_sample': balg,
-                'samples_per_launch': ev.shard.n_local,
-                'peak_source': f'{peak_kind} (MEASURED_PEAKS.json hbm_gbs, '
-                               'burst copy)',
-                'frac_of_nominal_8TBs': achieved / 8000.0},
-        }
-        if sync_ms is not None:
-            line['value_sync'] = sets / (sync_ms * 1e-3)
-            line['ms_per_step_sync'] = sync_ms / args.steps
-        if solver_api is not None:
-            line['e2e_solver_api'] = solver_api['pageable']
-            line['e2e_solver_api_pinned'] = solver_api['pinned']
-        if world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_baseline()
-        out.emit(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-    if not reduce_check['ok']:
-        raise SystemExit(f'reduce_check failed: {reduce_check}')
+    return e2e_ms, e2e_h2d, e2e_d2h, e2e_note, solver_api
 
 
 def check_reduction(h, ev, problem, dvec, ldvec, world, device, dist, torch):
@@ -723,8 +779,21 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    # other script shapes / strong scaling (profiles/ tables); the default
+    # line -- attas_sp_ml, (2,1,2), 1e6 samples per GPU, weak -- is untouched
+    ap.add_argument('--kind', default=KIND,
+                    help='problem family (families.make_problem)')
+    ap.add_argument('--dims', default=''.join(str(d) for d in DIMS),
+                    help='nx nu ny as three digits, e.g. 533')
+    ap.add_argument('--n-per-gpu', type=int, default=N_PER_GPU)
+    ap.add_argument('--n-total', type=int, default=0,
+                    help='strong scaling: fixed trajectory length split over '
+                         'the GPUs (overrides --n-per-gpu)')
+    ap.add_argument('--no-e2e', action='store_true',
+                    help='device-resident numbers only (table runs)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    configure_workload(args)
     with OneLineStdout() as out:
         if args.impl == 'reference':
             run_reference(args, out)

@@ -153,7 +153,7 @@ class Generator:
                 st = layout['stor'][key]
                 lines.append(
                     f'const double {ident} = {st["name"]}'
-                    f'[cfem::Skew<{st["core"]}>::row(tid + {ref[2]}) + {flat}];')
+                    f'[cfem::Skew<{st["core"]}>::row(row + {ref[2]}) + {flat}];')
         return lines, undefs
 
     # ------------------------------------------------------------------
@@ -384,16 +384,18 @@ class Generator:
                         w.append(f'        pat[{it.pat_off + j}] = {code};')
                     w += undefs
             w.append('    }')
+            w.append('    __syncthreads();       // the pattern table is built')
 
-        def stage(it_expr, buf_expr):
-            """cp.async of the rows of this CTA's tile ``it_expr`` into
-            staging buffer ``buf_expr``."""
+        def stage(item_expr, buf_expr):
+            """cp.async of the rows of work item ``item_expr`` into staging
+            buffer ``buf_expr``."""
             out = ['        {',
                    f'            double* const stg = smem + '
                    f'{lay["stage_off"]} + ({buf_expr}) * {lay["stage_stride"]};',
-                   f'            const long long r0 = CFEM_TILE_K0({it_expr});',
-                   f'            const int nr = 32 * CFEM_TILE_NW({it_expr});',
-                   '            (void)stg; (void)r0; (void)nr;']
+                   '            long long r0; int spw_;',
+                   f'            cfem::item_range(a, {item_expr}, r0, spw_);',
+                   f'            const int nr = spw_ * {T // 32};',
+                   '            (void)stg; (void)nr;']
             for key in sorted(lay['stor']):
                 st_ = lay['stor'][key]
                 if key[0] == 'var':
@@ -430,36 +432,51 @@ class Generator:
             '            if (tid == 0) a.done_count[b] = 0u;',
             '        }']
 
-        # Balanced persistent schedule (cfem_args.cuh): `rounds` full tiles
-        # it * gridDim.x + blockIdx.x, then one partial tile of tail_n
-        # warp-rows; the inputs of the next tile are in flight (cp.async)
-        # while this one is evaluated and streamed out.
-        w.append('    const long long G = gridDim.x, c = blockIdx.x;')
-        w.append('    const int tail_n = a.tail_q + (c < a.tail_rem ? 1 : 0);')
-        w.append('    const long long tail_k0 = (a.tail_base + c * a.tail_q + '
-                 '(c < a.tail_rem ? c : (long long)a.tail_rem)) * 32;')
-        w.append('    const int nit = (int)a.rounds + (tail_n > 0 ? 1 : 0);')
-        w.append(f'#define CFEM_TILE_K0(it) ((it) < a.rounds ? ((it) * G + c) '
-                 f'* {T} : tail_k0)')
-        w.append(f'#define CFEM_TILE_NW(it) ((it) < a.rounds ? {T // 32} : '
-                 'tail_n)')
+        # Work items (cfem_args.cuh): CTA c takes items c, c + gridDim.x, ...;
+        # the inputs of the next item are in flight (cp.async) while this one
+        # is evaluated and streamed out.  Per item: (1) the sample-independent
+        # blocks are streamed from the pattern table -- they need no input,
+        # so these stores overlap the latency of the item's own loads; (2)
+        # wait for the loads; (3) the reduction (last item only); (4) the
+        # sample-dependent blocks.
+        w.append('    const long long G = gridDim.x;')
         w.append('    int buf = 0;')
-        w.append('    if (nit > 0)')
-        w += stage('0', '0')
+        w.append('    long long item = blockIdx.x;')
+        w.append('    if (item < a.nitems)')
+        w += stage('item', '0')
         w.append('    cfem::cp_async_commit();')
-        w.append('    for (int it = 0; it < nit; ++it, buf ^= 1) {')
-        w.append('    if (it + 1 < nit)')
-        w += stage('it + 1', 'buf ^ 1')
+        w.append('    for (; item < a.nitems; item += G, buf ^= 1) {')
+        w.append('    const bool last_item = item + G >= a.nitems;')
+        w.append('    if (!last_item)')
+        w += stage('item + G', 'buf ^ 1')
         w.append('    cfem::cp_async_commit();')
-        w.append('    cfem::cp_async_wait<1>();      // this tile has landed')
+        w.append('    long long k0; int spw;')
+        w.append('    cfem::item_range(a, item, k0, spw);')
+        w.append('    const long long kw = k0 + warp * spw;    // first sample '
+                 'of this warp')
+        w.append('    const int row = warp * spw + lane;        // row of this '
+                 'thread in the staged item')
+        w.append('    (void)kw; (void)row;')
+        for p in plan:
+            if not p['uniform']:
+                continue
+            fi = p['fi']
+            w.append('    {')
+            w.append(f'        const long long left = a.fun_rows[{fi}] - kw;')
+            w.append('        const int nvalid = left >= spw ? spw : '
+                     '(left > 0 ? (int)left : 0);')
+            w.append('        if (nvalid > 0) {')
+            for it in p['uniform']:
+                w.append(f'            cfem::warp_store_periodic<{it.c}>(pat + '
+                         f'{it.pat_off}, lane, ({it.dest}) + kw * {it.c}, '
+                         'nvalid);')
+            w.append('        }')
+            w.append('    }')
+        w.append('    cfem::cp_async_wait<1>();      // this item has landed')
         w.append('    __syncthreads();')
         w.append(f'    double* const stg = smem + {lay["stage_off"]} + buf * '
                  f'{lay["stage_stride"]};')
-        w.append('    const long long k0 = CFEM_TILE_K0(it);')
-        w.append('    const long long kend = k0 + 32 * CFEM_TILE_NW(it);')
-        w.append('    const long long kw = k0 + warp * 32;')
-        w.append('    const long long k = k0 + tid;')
-        w.append('    (void)stg; (void)kw; (void)k; (void)kend;')
+        w.append('    (void)stg;')
         for key in sorted(lay['stor']):
             st_ = lay['stor'][key]
             w.append(f'    const double* const {st_["name"]} = stg + '
@@ -471,12 +488,10 @@ class Generator:
 
             def open_block():
                 w.append('    {')
-                w.append(f'        const long long M = a.fun_rows[{fi}] < kend'
-                         f' ? a.fun_rows[{fi}] : kend;')
-                w.append('        const long long left = M - kw;')
-                w.append('        const int nvalid = left >= 32 ? 32 : '
+                w.append(f'        const long long left = a.fun_rows[{fi}] - kw;')
+                w.append('        const int nvalid = left >= spw ? spw : '
                          '(left > 0 ? (int)left : 0);')
-                w.append('        const bool act = k < M;')
+                w.append('        const bool act = lane < nvalid;')
                 w.append('        (void)act;')
                 w.append('        if (nvalid > 0) {')
                 w.extend('        ' + d if d.startswith('#')
@@ -495,21 +510,17 @@ class Generator:
                              f'act ? ({code}) : 0.0;')
                 close_block()
             if pi == red_after:
-                w.append('    if (it + 1 == nit) {')
+                w.append('    if (last_item) {')
                 w += reduce_call
                 w.append('    }')
-            if not (p['items'] or p['uniform']):
+            if not p['passes']:
                 continue
             open_block()
             if p['lam']:
                 s = lay['stor'][('lam', fi)]
                 for o in range(f['out_core']):
                     w.append(f'            const double lam_{fi}_{o} = '
-                             f'{s["name"]}[cfem::Skew<{s["core"]}>::row(tid) + {o}];')
-            for it in p['uniform']:
-                w.append(f'            cfem::warp_store_periodic<{it.c}>(pat + '
-                         f'{it.pat_off}, lane, ({it.dest}) + kw * {it.c}, '
-                         'nvalid);')
+                             f'{s["name"]}[cfem::Skew<{s["core"]}>::row(row) + {o}];')
             for ps in p['passes']:
                 wboff = 0
                 staged = []
@@ -540,20 +551,14 @@ class Generator:
                                  'nvalid);')
                     w.append('            __syncwarp();')
             close_block()
-        w.append('    if (it + 1 < nit) __syncthreads();   // staging buffer '
+        w.append('    if (!last_item) __syncthreads();   // staging buffer '
                  'is refilled by the next prefetch')
-        w.append('    }   // tile loop')
-        if has_red:
-            # CTAs without a tile, and kernels whose reductions have no
-            # per-sample term, still take part in the tree
-            if red_after >= 0:
-                w.append('    if (nit == 0) {')
-            else:
-                w.append('    {')
+        w.append('    }   // item loop')
+        if has_red and red_after < 0:
+            # reductions without a per-sample term still go through the tree
+            w.append('    {')
             w += reduce_call
             w.append('    }')
-        w.append('#undef CFEM_TILE_K0')
-        w.append('#undef CFEM_TILE_NW')
         w.append('    // programmatic dependent launch: the parameter-only '
                  'kernel is the prerequisite grid;')
         w.append('    // nothing here reads its results, but a completed '
@@ -929,7 +934,7 @@ class Generator:
                  'const int tid, double* scratch)')
         w.append('{')
         w.append('    const double* __restrict__ dvec = a.dvec + b * a.ndec;')
-        w.append(f'    const double* part = a.gpartials + b * a.ngroups * {nd};')
+        w.append(f'    const double* part = a.gpartials + b * a.group_stride * {nd};')
         w.append(f'    double tot[{R}];')
         w.append(f'    for (int r = 0; r < {R}; ++r) tot[r] = 0.0;')
         for di, slot in enumerate(self.dyn_slots):
@@ -1183,60 +1188,86 @@ class Generator:
                  'g_single_buf = atoi(v) != 0;')
         w.append('    return e;')
         w.append('}')
-        w.append('// Balanced persistent launch: one resident set of CTAs per '
-                 'problem (x `waves`), every CTA')
-        w.append('// gets the same number of 32-sample warp-rows to within one '
-                 '(cfem_args.cuh).  The CTA')
-        w.append('// count is the same for every kernel variant of the library '
-                 '(the smallest residency),')
-        w.append('// so the fixed-order reductions give the same bits whichever '
-                 'variant serves a callback.')
-        w.append('// When that covers every tile (one tile per CTA) the second '
-                 'staging buffer is')
-        w.append('// not allocated: less shared memory per CTA, more resident '
-                 'CTAs per SM.')
-        w.append('static void prepare_sample(unsigned mask, int batch, '
-                 'int sm_count, int waves, '
-                 'cfem::KArgs& a, dim3& grid, size_t& smem)')
-        w.append('{')
-        w.append('    int idx = 0, per_sm1 = 1 << 30, per_sm2 = 1 << 30;')
-        w.append('    for (int i = 0; i < kNumMasks; ++i) {')
-        w.append('        if (kMasks[i] == mask) idx = i;')
-        w.append('        if (g_ctas_per_sm1[i] < per_sm1) per_sm1 = g_ctas_per_sm1[i];')
-        w.append('        if (g_ctas_per_sm[i] < per_sm2) per_sm2 = g_ctas_per_sm[i];')
-        w.append('    }')
-        w.append('    long long gx = (long long)per_sm1 * sm_count * waves / batch;')
-        w.append('    smem = kSmem1[idx];')
-        w.append('    if (!g_single_buf || gx < a.ntiles) {     '
-                 '// several tiles per CTA: double buffering')
-        w.append('        gx = (long long)per_sm2 * sm_count * waves / batch;')
-        w.append('        smem = kSmem2[idx];')
-        w.append('    }')
-        w.append('    if (gx < 1) gx = 1;')
-        w.append('    if (gx > a.ntiles) gx = a.ntiles;')
-        w.append('    a.nctas = gx;')
-        w.append('    const long long wpt = CFEM_TILE / 32, wr = (a.N + 31) / 32;')
-        w.append('    a.rounds = wr / (gx * wpt);')
-        w.append('    a.tail_base = a.rounds * gx * wpt;')
-        w.append('    const long long left = wr - a.tail_base;    // < gx * wpt')
-        w.append('    a.tail_q = (int)(left / gx);')
-        w.append('    a.tail_rem = (int)(left % gx);')
-        w.append('    a.ngroups = (gx + cfem::kReduceGroup - 1) / '
-                 'cfem::kReduceGroup;')
-        w.append('    grid = dim3((unsigned)gx, (unsigned)batch);')
-        w.append('}')
+        w.append("""// Work items of one launch (cfem_args.cuh).  Full tiles first; when there is
+// enough work, the last two resident sets are half and quarter tiles (graded
+// tail): the CTAs that run last -- their slots are not refilled -- are short,
+// so the grid drains in a fraction of a tile time.  `resident` = CTAs of this
+// problem that fit on the GPU at once.
+static void build_items(long long resident, int tail_levels, cfem::KArgs& a)
+{
+    const long long T = CFEM_TILE, N = a.N;
+    const int min_size = 8 * (CFEM_TILE / 32);
+    int sizes[cfem::kMaxPhases];
+    int np = 1;
+    sizes[0] = CFEM_TILE;
+    while (np < cfem::kMaxPhases && np <= tail_levels && sizes[np - 1] / 2 >= min_size) {
+        sizes[np] = sizes[np - 1] / 2;
+        ++np;
+    }
+    long long tail = 0;
+    for (int p = 1; p < np; ++p) tail += resident * sizes[p];
+    if (np == 1 || N < tail + 2 * resident * T) {      // not worth grading
+        a.nphase = 1;
+        a.ph_item0[0] = 0; a.ph_k0[0] = 0; a.ph_size[0] = CFEM_TILE;
+        a.nitems = (N + T - 1) / T;
+        return;
+    }
+    a.nphase = np;
+    long long item = 0, k0 = 0;
+    for (int p = 0; p < np; ++p) {
+        a.ph_item0[p] = item; a.ph_k0[p] = k0; a.ph_size[p] = sizes[p];
+        long long count = p == 0 ? (N - tail) / T : resident;
+        if (p == np - 1) count = (N - k0 + sizes[p] - 1) / sizes[p];   // the rest
+        item += count;
+        k0 += count * sizes[p];
+    }
+    a.nitems = item;
+}
+// Launch geometry: at most `waves` resident sets of CTAs per problem, CTA c
+// takes items c, c + nctas, ...  The CTA count is the same for every kernel
+// variant of the library (the smallest residency), so the fixed-order
+// reductions give the same bits whichever variant serves a callback.  When
+// every CTA has exactly one item the second staging buffer is not allocated:
+// less shared memory per CTA, more resident CTAs per SM.
+static void prepare_sample(unsigned mask, int batch, int sm_count, int waves, int tail_levels,
+                           cfem::KArgs& a, dim3& grid, size_t& smem)
+{
+    int idx = 0, per_sm1 = 1 << 30, per_sm2 = 1 << 30;
+    for (int i = 0; i < kNumMasks; ++i) {
+        if (kMasks[i] == mask) idx = i;
+        if (g_ctas_per_sm1[i] < per_sm1) per_sm1 = g_ctas_per_sm1[i];
+        if (g_ctas_per_sm[i] < per_sm2) per_sm2 = g_ctas_per_sm[i];
+    }
+    long long resident = (long long)per_sm1 * sm_count / batch;
+    if (resident < 1) resident = 1;
+    build_items(resident, tail_levels, a);
+    long long gx = resident * waves;
+    smem = kSmem1[idx];
+    if (!g_single_buf || gx < a.nitems) {       // several items per CTA: double buffering
+        resident = (long long)per_sm2 * sm_count / batch;
+        if (resident < 1) resident = 1;
+        build_items(resident, tail_levels, a);
+        gx = resident * waves;
+        smem = kSmem2[idx];
+    }
+    if (gx > a.nitems) gx = a.nitems;
+    if (gx > a.part_stride) gx = a.part_stride;     // partial-sum slots (cfem_create)
+    a.nctas = gx;
+    a.ngroups = (gx + cfem::kReduceGroup - 1) / cfem::kReduceGroup;
+    grid = dim3((unsigned)gx, (unsigned)batch);
+}""")
         w.append('// overlap_prev: programmatic stream serialisation -- the kernel '
                  'may start while the')
         w.append('// preceding kernel of the stream (the parameter-only kernel, '
                  'no data dependence)')
         w.append('// is still running.')
         w.append('static cudaError_t launch_sample(unsigned mask, int batch, '
-                 'int sm_count, int waves, bool overlap_prev, '
+                 'int sm_count, int waves, int tail_levels, bool overlap_prev, '
                  'cudaStream_t s, cfem::KArgs a)')
         w.append('{')
         w.append('    cudaLaunchConfig_t cfg = {};')
         w.append('    size_t smem = 0;')
-        w.append('    prepare_sample(mask, batch, sm_count, waves, a, cfg.gridDim, smem);')
+        w.append('    prepare_sample(mask, batch, sm_count, waves, tail_levels, a, cfg.gridDim, smem);')
         w.append('    cfg.dynamicSmemBytes = smem;')
         w.append('    cfg.blockDim = dim3(CFEM_TILE);')
         w.append('    cfg.stream = s;')

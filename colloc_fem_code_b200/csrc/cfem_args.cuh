@@ -8,6 +8,7 @@
 namespace cfem {
 
 constexpr int kMaxPeers = 16;
+constexpr int kMaxPhases = 4;
 
 template <int N> struct AtLeastOne { static constexpr int value = N > 0 ? N : 1; };
 
@@ -28,20 +29,26 @@ struct KArgs {
     double* g;
     double* jac;
     double* hess;
-    double* partials;       // [batch][ntiles][nreduce]
+    double* partials;       // [batch][part_stride][nreduce]
     // two-level deterministic reduction tree (all counters zero between launches)
-    long long     nctas;        // CTAs per problem of this launch (<= ntiles)
-    // Balanced persistent schedule in units of warp-rows (32 samples): CTA c
-    // runs `rounds` full tiles (it * nctas + c) and then ONE partial tile of
-    // tail_q (+1 for c < tail_rem) warp-rows, so that every CTA of a problem
-    // gets the same number of samples to within one warp-row and the CTAs
-    // retire together (no half-empty last wave, no drain).
-    long long     rounds;       // full tiles per CTA
-    long long     tail_base;    // first warp-row of the partial tiles
-    int           tail_q, tail_rem;
+    long long     nctas;        // CTAs per problem of this launch (<= part_stride)
+    long long     part_stride;  // partial-sum slots per problem: partials [batch][part_stride][nreduce]
+    long long     group_stride; // ceil(part_stride / kReduceGroup): gpartials / group_count rows per problem
+    // Work items: item i covers samples [k0, k0 + size), size a multiple of
+    // 8 * warps per CTA.  The items come in up to kMaxPhases phases of
+    // decreasing size -- full tiles of CFEM_TILE samples first, then one
+    // resident set of half tiles, then quarter tiles ... (cfem_host: graded
+    // tail) -- so that the CTAs of the LAST resident set, whose slots are not
+    // refilled, are short: the grid drains in a fraction of a tile time.
+    // CTA c takes items c, c + nctas, ...
+    long long     nitems;
+    int           nphase;
+    long long     ph_item0[kMaxPhases];     // first item of the phase
+    long long     ph_k0[kMaxPhases];        // first sample of the phase
+    int           ph_size[kMaxPhases];      // samples per item
     long long     ngroups;      // ceil(nctas / kReduceGroup)
-    double*       gpartials;    // [batch][ngroups][nreduce]
-    unsigned int* group_count;  // [batch][ngroups] CTAs retired per group
+    double*       gpartials;    // [batch][group_stride][nreduce]
+    unsigned int* group_count;  // [batch][group_stride] CTAs retired per group
     unsigned int* done_count;   // [batch] groups retired per problem
     // fused cross-GPU reduction over peer memory (time-sharded runs)
     int                 peer_rank, peer_world;      // world <= 1: disabled

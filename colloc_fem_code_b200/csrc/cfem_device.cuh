@@ -139,6 +139,18 @@ __device__ __forceinline__ void stage_rows_async(double* __restrict__ dst,
     }
 }
 
+// Work item -> first sample and samples per warp (cfem_args.cuh).
+__device__ __forceinline__ void item_range(const KArgs& a, long long item,
+                                           long long& k0, int& spw)
+{
+    int p = 0;
+#pragma unroll
+    for (int q = 1; q < kMaxPhases; ++q)
+        if (q < a.nphase && item >= a.ph_item0[q]) p = q;
+    k0 = a.ph_k0[p] + (item - a.ph_item0[p]) * a.ph_size[p];
+    spw = a.ph_size[p] / kWarpsPerCta;
+}
+
 // ---------------------------------------------------------------------------
 // per-warp output transposition
 // ---------------------------------------------------------------------------
@@ -319,18 +331,18 @@ __device__ __forceinline__ bool tree_reduce(const KArgs& a, long long b,
                                             int tid)
 {
     const long long cta = blockIdx.x;       // one partial per (persistent) CTA
-    block_reduce_store<R>(v, scratch, a.partials + (b * a.ntiles + cta) * R, tid);
+    block_reduce_store<R>(v, scratch, a.partials + (b * a.part_stride + cta) * R, tid);
     const long long g = cta / kReduceGroup;
     const long long first = g * kReduceGroup;
     const long long left = a.nctas - first;
     const unsigned in_group = left < kReduceGroup ? (unsigned)left : (unsigned)kReduceGroup;
-    unsigned int* gcount = a.group_count + b * a.ngroups + g;
+    unsigned int* gcount = a.group_count + b * a.group_stride + g;
     if (!last_block_done(gcount, in_group, tid)) return false;
-    const double* part = a.partials + (b * a.ntiles + first) * R;
+    const double* part = a.partials + (b * a.part_stride + first) * R;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const double s = reduce_tiles<CFEM_TILE>(part, in_group, R, r, scratch, tid);
-        if (tid == 0) a.gpartials[(b * a.ngroups + g) * R + r] = s;
+        if (tid == 0) a.gpartials[(b * a.group_stride + g) * R + r] = s;
     }
     if (tid == 0) {
         *gcount = 0u;

@@ -12,6 +12,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
 #include <atomic>
 #include <condition_variable>
 #include <mutex>
@@ -29,6 +33,35 @@ namespace cfem {
 // PCIe link moves ~55 GB/s, so the staging copy is sliced over a few persistent
 // worker threads and pipelined chunk by chunk against the DMA transfers
 // (staged_d2h / staged_h2d below).
+// memcpy with non-temporal stores: the destination of a staging copy is not
+// read again by this core, so it should neither be fetched into the cache
+// first (read-for-ownership) nor evict the rest of it.  glibc switches to
+// streaming stores only far above the slice sizes used here.
+static inline void copy_streaming(char* dst, const char* src, size_t n)
+{
+#if defined(__x86_64__)
+    size_t head = (size_t)((16 - ((uintptr_t)dst & 15)) & 15);
+    if (head > n) head = n;
+    memcpy(dst, src, head);
+    dst += head; src += head; n -= head;
+    const size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks; ++i) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)(src + 64 * i));
+        const __m128i b = _mm_loadu_si128((const __m128i*)(src + 64 * i + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i*)(src + 64 * i + 32));
+        const __m128i d = _mm_loadu_si128((const __m128i*)(src + 64 * i + 48));
+        _mm_stream_si128((__m128i*)(dst + 64 * i), a);
+        _mm_stream_si128((__m128i*)(dst + 64 * i + 16), b);
+        _mm_stream_si128((__m128i*)(dst + 64 * i + 32), c);
+        _mm_stream_si128((__m128i*)(dst + 64 * i + 48), d);
+    }
+    _mm_sfence();
+    memcpy(dst + 64 * blocks, src + 64 * blocks, n - 64 * blocks);
+#else
+    memcpy(dst, src, n);
+#endif
+}
+
 class CopyPool {
 public:
     explicit CopyPool(int nthreads) : n_(nthreads < 1 ? 1 : nthreads)
@@ -45,7 +78,7 @@ public:
     // blocks until all slices are copied (the caller copies slice 0)
     void copy(void* dst, const void* src, size_t bytes)
     {
-        if (n_ == 1 || bytes < (size_t)(1 << 20)) { memcpy(dst, src, bytes); return; }
+        if (n_ == 1 || bytes < (size_t)(1 << 20)) { copy_streaming((char*)dst, (const char*)src, bytes); return; }
         {
             std::lock_guard<std::mutex> lk(m_);
             dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes;
@@ -64,7 +97,7 @@ private:
         const size_t lo = per * i;
         if (lo >= bytes_) return;
         const size_t len = bytes_ - lo < per ? bytes_ - lo : per;
-        memcpy(dst_ + lo, src_ + lo, len);
+        copy_streaming(dst_ + lo, src_ + lo, len);
     }
     void loop(int i)
     {
@@ -96,7 +129,8 @@ private:
 struct cfem_problem {
     int           device = 0;
     int           sm_count = 1;
-    int           waves = 1;            // CTAs launched <= resident CTAs x waves (balanced persistent schedule)
+    int           waves = 8;            // CTAs launched <= resident CTAs x waves (B200 sweeps: the hardware CTA dispatcher balances SMs of different speed)
+    int           tail_levels = 2;      // graded tail: one resident set of half tiles, one of quarter tiles (CFEM_TAIL_LEVELS)
     cudaStream_t  stream = nullptr;
     bool          own_stream = false;
     cudaStream_t  aux_stream = nullptr;     // parameter-only kernel, concurrent
@@ -420,6 +454,7 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     p->device = device;
     p->sm_count = sm_count;
     if (const char* w = getenv("CFEM_WAVES")) { p->waves = atoi(w) > 0 ? atoi(w) : 1; }
+    if (const char* w = getenv("CFEM_TAIL_LEVELS")) { p->tail_levels = atoi(w) >= 0 ? atoi(w) : 0; }
     if (const char* w = getenv("CFEM_PDL")) { p->use_pdl = atoi(w); }
     if (const char* w = getenv("CFEM_GRAPH")) { p->use_graph = atoi(w) != 0; }
     if (const char* w = getenv("CFEM_COPY_THREADS")) { p->copy_threads = atoi(w) > 0 ? atoi(w) : 1; }
@@ -439,7 +474,11 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     memset(&k, 0, sizeof k);
     k.N = n_samples;
     k.ntiles = (n_samples + CFEM_TILE - 1) / CFEM_TILE;
-    k.ngroups = (k.ntiles + cfem::kReduceGroup - 1) / cfem::kReduceGroup;
+    // one partial-sum slot per CTA: the graded tail adds at most ~1.25 resident
+    // sets of items (<= 32 CTAs per SM) to the tile count
+    k.part_stride = k.ntiles + 2ll * 32 * sm_count;
+    k.group_stride = (k.part_stride + cfem::kReduceGroup - 1) / cfem::kReduceGroup;
+    k.ngroups = k.group_stride;
     k.ndec = L.ndec; k.ncons = L.ncons; k.nnz_jac = L.nnz_jac; k.nnz_hess = L.nnz_hess;
     k.nreduce = gen::kNumReduce;
     k.obj_factor = 1.0;
@@ -493,11 +532,11 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     k.g = p->d_results + p->res_off[2];
     k.jac = p->d_results + p->res_off[3];
     k.hess = p->d_results + p->res_off[4];
-    CFEM_TRY(cudaMalloc(&k.partials, B * k.ntiles * gen::kNumDynReduce * D));
+    CFEM_TRY(cudaMalloc(&k.partials, B * k.part_stride * gen::kNumDynReduce * D));
     CFEM_TRY(cudaMalloc(&k.reduce, B * gen::kNumReduce * D));
-    CFEM_TRY(cudaMalloc(&k.gpartials, B * k.ngroups * gen::kNumDynReduce * D));
-    CFEM_TRY(cudaMalloc(&k.group_count, B * k.ngroups * sizeof(unsigned int)));
-    CFEM_TRY(cudaMemset(k.group_count, 0, B * k.ngroups * sizeof(unsigned int)));
+    CFEM_TRY(cudaMalloc(&k.gpartials, B * k.group_stride * gen::kNumDynReduce * D));
+    CFEM_TRY(cudaMalloc(&k.group_count, B * k.group_stride * sizeof(unsigned int)));
+    CFEM_TRY(cudaMemset(k.group_count, 0, B * k.group_stride * sizeof(unsigned int)));
     CFEM_TRY(cudaMalloc(&k.done_count, B * sizeof(unsigned int)));
     CFEM_TRY(cudaMemset(k.done_count, 0, B * sizeof(unsigned int)));
     // structurally-zero gradient entries are written once, here
@@ -621,7 +660,7 @@ static int cfem_launch_graph(cfem_problem* p, unsigned mask, bool params)
     cfem::KArgs a1 = p->k;
     dim3 grid;
     size_t smem = 0;
-    gen::prepare_sample(mask, p->batch, p->sm_count, p->waves, a1, grid, smem);
+    gen::prepare_sample(mask, p->batch, p->sm_count, p->waves, p->tail_levels, a1, grid, smem);
     if (g.exec && g.params != params) {         // CFEM_SKIP_PARAM toggled: rebuild
         cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph);
         g = cfem_problem::StepGraph();
@@ -636,7 +675,7 @@ static int cfem_launch_graph(cfem_problem* p, unsigned mask, bool params)
             if (e == cudaSuccess) e = cudaEventRecord(p->ev_join, p->aux_stream);
         }
         if (e == cudaSuccess)
-            e = gen::launch_sample(mask, p->batch, p->sm_count, p->waves, false, p->stream, p->k);
+            e = gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->tail_levels, false, p->stream, p->k);
         if (e == cudaSuccess && params) e = cudaStreamWaitEvent(p->stream, p->ev_join, 0);
         cudaGraph_t graph = nullptr;
         cudaError_t e2 = cudaStreamEndCapture(p->stream, &graph);
@@ -722,7 +761,7 @@ int cfem_eval(cfem_problem* p, uint32_t what)
         // the native trajectory lengths, where one evaluation is 15-40 us, the
         // two launches start about 1 us earlier from two streams (fork/join).
         CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->stream, p->k));
-        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, true, p->stream, p->k));
+        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->tail_levels, true, p->stream, p->k));
     } else {
         if (params) {
             CFEM_CUDA(p, cudaEventRecord(p->ev_fork, p->stream));
@@ -731,7 +770,7 @@ int cfem_eval(cfem_problem* p, uint32_t what)
             CFEM_CUDA(p, cudaEventRecord(p->ev_join, p->aux_stream));
         }
         if (p->timing) CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot], p->stream));
-        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, false, p->stream, p->k));
+        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->tail_levels, false, p->stream, p->k));
         if (p->timing) {
             CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot + 1], p->stream));
             p->kev_count += 1;

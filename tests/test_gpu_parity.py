@@ -14,7 +14,8 @@ from oracle import ref_models
 
 pytestmark = pytest.mark.gpu
 
-from parity_helpers import RTOL, check_against, exact_masks
+from parity_helpers import (RTOL, check_against, exact_masks,
+                            grad_sample_mask)
 from parity_helpers import scale_of as _scale
 
 MASKS = (1, 3, 4, 8, 16, 5, 15, 31)
@@ -102,9 +103,20 @@ def test_random_point_vs_oracle(kind, dims, N):
     dvec, lam, _ = synthetic.evaluation_point(p, exp, seed=N)
     sigma = 0.8
     scale = _scale(dvec, exp['y'], exp['u']) ** 2 * (nx + nu + ny + 1)
-    check_against(cuda_callbacks(p, dvec, sigma, lam),
-                  oracle_callbacks(o, dvec, sigma, lam), scale,
-                  exact_masks(p))
+    res = cuda_callbacks(p, dvec, sigma, lam)
+    check_against(res, oracle_callbacks(o, dvec, sigma, lam), scale,
+                  exact_masks(p), (grad_sample_mask(p), N))
+    # the summed parameter entries against their closed form (adfem.py:119:
+    # sum over samples of -1 / sRp_ii), at the stated 1e-12
+    if kind != 'trapezoid':
+        var = p.variables(dvec)
+        diag = var['sRp_tril'][families.models.tril_diag(ny)]
+        sl = p.decision['sRp_tril']
+        got = res['grad'][sl.offset:sl.offset + sl.size][
+            families.models.tril_diag(ny)]
+        np.testing.assert_allclose(got, -N / diag, rtol=RTOL)
+        f_ref = -0.5 * np.sum(var['en'] ** 2) - N * np.log(diag).sum()
+        np.testing.assert_allclose(res['f'], f_ref, rtol=RTOL)
 
 
 def test_bench_workload_vs_oracle():
@@ -121,7 +133,7 @@ def test_bench_workload_vs_oracle():
     scale = _scale(dvec, exp['y'], exp['u']) ** 2 * (nx + nu + ny + 1)
     check_against({'f': f, 'grad': grad, 'g': g, 'jac': jac, 'hess': hess},
                   oracle_callbacks(o, dvec, sigma, lam), scale,
-                  exact_masks(p))
+                  exact_masks(p), (grad_sample_mask(p), N))
 
 
 def test_known_answer_noise_free():

@@ -29,8 +29,7 @@ if os.environ.get('SWEEP_SET', 'occupancy') == 'store':
 elif os.environ.get('SWEEP_SET') == 'r2':
     # round 2: balanced persistent schedule (waves = 1, 2) against one tile
     # per CTA (waves = 8), tile size x launch bounds
-    for tile, mbs in ((128, (None, 7, 8)), (64, (None, 14, 16)),
-                      (256, (None, 3, 4))):
+    for tile, mbs in ((128, (None, 8)), (64, (None,)), (256, (None, 4))):
         for mb in mbs:
             VARIANTS.append(dict(tile=tile, pass_budget=6, min_blocks=mb))
 else:       # resident CTAs per SM: launch bounds x single staging buffer
@@ -40,6 +39,7 @@ else:       # resident CTAs per SM: launch bounds x single staging buffer
             VARIANTS.append(dict(tile=tile, pass_budget=6, min_blocks=mb))
 SINGLE = [int(v) for v in os.environ.get('SWEEP_SINGLE_BUF', '1,0').split(',')]
 WAVES = [int(w) for w in os.environ.get('SWEEP_WAVES', '4,8').split(',')]
+TAILS = [int(w) for w in os.environ.get('SWEEP_TAILS', '2').split(',')]
 
 
 def problem():
@@ -73,8 +73,10 @@ def run():
     import bench
     balg = bench.algorithmic_bytes_per_sample(nx, nu, ny)
     out = []
-    for v, waves, single in itertools.product(VARIANTS, WAVES, SINGLE):
+    for v, waves, single, tail in itertools.product(VARIANTS, WAVES, SINGLE,
+                                                    TAILS):
         os.environ['CFEM_WAVES'] = str(waves)
+        os.environ['CFEM_TAIL_LEVELS'] = str(tail)
         os.environ['CFEM_SINGLE_BUF'] = str(single)
         lib = backend.Library.load(backend.build_library(
             st, backend.structure_label(st), masks=(31,), **v))
@@ -92,7 +94,7 @@ def run():
             ms.append(h.last_sample_kernel_ms())
         ms = ms[3:]
         f_val = float(h.fetch(1)[0])        # sanity: the same objective everywhere
-        rec = dict(v, waves=waves, single_buf=single, ms_min=min(ms), ms_med=float(np.median(ms)), f=f_val,
+        rec = dict(v, waves=waves, single_buf=single, tail_levels=tail, ms_min=min(ms), ms_med=float(np.median(ms)), f=f_val,
                    gbs=balg * N / (np.median(ms) * 1e-3) / 1e9)
         print(json.dumps(rec), flush=True)
         out.append(rec)
