@@ -181,8 +181,18 @@ def stale_variable_aliases(var):
 class _StaleVariables:
     """Problem mixin: ``variables()`` also answers to the stale names."""
 
+    #: variables the older code stored transposed (orthonormal COLUMNS:
+    #: hfb320_sqrt_zoh.py:123 assigns ``np.eye(2*nx, nx)`` to ``pred_orth``;
+    #: HEAD has orthonormal rows, symfem.py:145-149); handed out as
+    #: transposed, writable views of the same storage
+    stale_transposed = ()
+
     def variables(self, dvec):
-        return stale_variable_aliases(super().variables(dvec))
+        var = stale_variable_aliases(super().variables(dvec))
+        for name in self.stale_transposed:
+            if name in var:
+                var[name] = np.swapaxes(var[name], -1, -2)
+        return var
 
 
 def _stale_classes():
@@ -197,7 +207,8 @@ def _stale_classes():
         'NaturalSqrtZOHProblem': type(
             'NaturalSqrtZOHProblem',
             (_StaleVariables, problems.DiscretizedNoiseProblem,
-             problems.ZOHDynamicsProblem), {}),
+             problems.ZOHDynamicsProblem),
+            {'stale_transposed': ('pred_orth', 'corr_orth')}),
         # blackbox_innov_bal.py:32,55,59 -> BalancedDT
         'InnovationBalDTModel': type('InnovationBalDTModel',
                                      (models.BalancedDTModel,), {}),

@@ -74,3 +74,132 @@ print('ok')
     out = subprocess.run([sys.executable, '-c', code], capture_output=True,
                          text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-3000:]
+
+
+STALE_RUNNER = r'''
+import os, sys, warnings
+import numpy as np
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, 'tests'))
+import colloc_fem_code_b200.compat as compat
+compat.install(mirrors=True)        # the stale classes live on the mirrors
+from colloc_fem_code_b200 import nlp, synthetic
+from oracle import ref_models
+from nlp_helpers import OracleEvaluator
+
+# No GPU in this test: the callbacks come from the CPU oracle of the same
+# problem family (the layouts are identical, tests/test_host_layout.py).
+KIND = {'NaturalSqrtZOHProblem': 'ndisc_zoh', 'InnovationBalDTProblem': 'balanced'}
+def cpu_evaluator(problem):
+    o = ref_models.make_problem(KIND[type(problem).__name__], problem.y,
+                                problem.u, problem.model.nx,
+                                dt=getattr(problem.model, 'dt', 0.1))
+    assert (o.ndec, o.ncons) == (problem.ndec, problem.ncons)
+    return OracleEvaluator(o)
+nlp.GpuEvaluator = cpu_evaluator
+cap = nlp.Solver.add_int_option
+def capped(self, key, value):       # the point is to execute, not to converge
+    cap(self, key, min(value, 12) if key == 'max_iter' else value)
+nlp.Solver.add_int_option = capped
+
+src = open(%(script)r).read().split('\n')
+main_at = next(i for i, l in enumerate(src) if l.startswith("if __name__ == '__main__':"))
+ns = {'__name__': 'stale_script', '__file__': %(script)r}
+exec(compile('\n'.join(src[:main_at]), %(script)r, 'exec'), ns)
+
+nx, nu, ny, N = %(dims)r
+exp = synthetic.experiment(3, N, nx, nu, ny)
+files = {}
+if %(which)r == 'hfb320':
+    ns['load_data'] = lambda: (0.1 * np.arange(N), exp['u'], exp['y'])
+else:
+    from colloc_fem_code_b200 import fit
+    guess = fit.predictor_guess(exp['y'], exp['u'], exp['A'], exp['B'],
+                                exp['C'], exp['D'], np.zeros((nx, ny)))
+    sRp = np.zeros((ny, ny)); sRp[np.tril_indices(ny)] = guess['sRp_tril']
+    files = {'u.txt': exp['u'], 'y.txt': exp['y'], 'a.txt': exp['A'],
+             'b.txt': exp['B'], 'c.txt': exp['C'], 'd.txt': exp['D'],
+             'k.txt': guess['Ln'], 'xpred.txt': guess['x'],
+             'epred.txt': guess['en'], 'gram.txt': np.full(nx, 0.5),
+             'isRp.txt': np.linalg.inv(sRp)}
+    class NP:                       # np with the data files patched in
+        def __getattr__(self, name):
+            return getattr(np, name)
+        def loadtxt(self, path, *a, **k):
+            return np.array(files[os.path.basename(path)])
+    ns['np'] = NP()
+    ns['load_data'] = lambda: (exp['u'], exp['y'])
+
+first, last = %(lines)r            # 1-based, inclusive: the cited statement range
+body = src[main_at + 1:last]
+body = ['if True:'] + body
+with warnings.catch_warnings(record=True) as caught:
+    warnings.simplefilter('always')
+    exec(compile('\n'.join(body), %(script)r + ':main', 'exec'), ns)
+assert ns['problem'].ndec == len(ns['decopt'])
+assert np.all(np.isfinite(ns['decopt']))
+assert ns['eopt'].shape == (N, ny) and ns['L'].shape == (nx, ny)
+print('warnings:', sorted({str(w.message)[:60] for w in caught}))
+print('status:', ns['info']['status'], 'iterations:', ns['info'].get('iterations'))
+%(extra)s
+print('ok')
+'''
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, 'symfem.py')),
+                    reason='reference tree only exists in the build container')
+@pytest.mark.parametrize('which,script,dims,lines,extra', [
+    ('hfb320', 'hfb320_sqrt_zoh.py', (4, 2, 7, 40), (97, 204),
+     "assert ns['Qc'].shape == (4, 4) and ns['isRp'].shape == (7, 7)\n"
+     "assert type(ns['model']).__name__ == 'GeneratedNaturalSqrtZOHModel'"),
+    ('blackbox', 'blackbox_innov_bal.py', (5, 3, 3, 60), (55, 118),
+     "assert ns['W'].shape == (5, 5) and np.all(np.diag(ns['W']) >= 0)\n"
+     "assert np.all(np.isfinite(ns['isRp']))"),
+])
+def test_stale_script_bodies_execute(which, script, dims, lines, extra):
+    """hfb320_sqrt_zoh.py:97-204 and blackbox_innov_bal.py:55-118 -- class names
+    and variables of an older parametrisation -- run as written through
+    ``compat`` (stale classes, variable aliases, on-demand generated-model
+    modules), with the data loaders patched to synthetic arrays and the CPU
+    oracle serving the callbacks."""
+    code = STALE_RUNNER % {'root': ROOT, 'script': os.path.join(REF, script),
+                           'dims': dims, 'which': which, 'lines': lines,
+                           'extra': extra}
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True,
+                         text=True, timeout=900, cwd='/tmp')
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-4000:])
+    assert out.stdout.strip().endswith('ok')
+
+
+def test_stale_variable_views():
+    """L / e alias Ln / en; W_diag, isRp_tril, Qc are derived views."""
+    from colloc_fem_code_b200 import compat, models, problems
+    compat.add_stale_aliases()
+    m = models.NaturalSqrtZOHModel(nx=2, nu=1, ny=2).compile_class()()
+    m.dt = 0.1
+    p = problems.NaturalSqrtZOHProblem(m, np.zeros((6, 2)), np.zeros((6, 1)))
+    dec = np.zeros(p.ndec)
+    var = p.variables(dec)
+    var['L'][:] = 2.0
+    var['e'][:] = 3.0
+    assert (var['Ln'] == 2.0).all() and (p.variables(dec)['en'] == 3.0).all()
+    var['isRp_tril'][models.tril_diag(2)] = 1e2     # hfb320_sqrt_zoh.py:118
+    np.testing.assert_allclose(p.variables(dec)['sRp_tril'], [1e-2, 0, 1e-2])
+    var['Qc'][:] = np.eye(2) * 1e-2                 # hfb320_sqrt_zoh.py:125
+    np.testing.assert_allclose(p.variables(dec)['sQc_tril'], [0.1, 0, 0.1])
+    np.testing.assert_allclose(np.asarray(p.variables(dec)['Qc']),
+                               np.eye(2) * 1e-2)
+    # a bounds vector: nothing to transfer, the HEAD block keeps its value
+    lo = np.full(p.ndec, -np.inf)
+    with pytest.warns(UserWarning, match='older parametrisation'):
+        p.variables(lo)['isRp_tril'][models.tril_diag(2)] = 0
+    assert np.isinf(p.variables(lo)['sRp_tril']).all()
+    mb = models.InnovationBalDTModel(nx=2, nu=1, ny=2).compile_class()()
+    pb = problems.InnovationBalDTProblem(mb, np.zeros((6, 2)),
+                                         np.zeros((6, 1)))
+    decb = np.zeros(pb.ndec)
+    pb.variables(decb)['W_diag'][:] = [4.0, 9.0]    # blackbox_innov_bal.py:72
+    np.testing.assert_allclose(pb.variables(decb)['sW_diag'], [2.0, 3.0])
+    lob = np.full(pb.ndec, -np.inf)
+    pb.variables(lob)['W_diag'][:] = 0              # blackbox_innov_bal.py:80
+    assert (pb.variables(lob)['sW_diag'] == 0).all()
