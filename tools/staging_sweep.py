@@ -50,6 +50,7 @@ def main():
             h.set_dvec(x)
             h.synchronize()
             h2d.append(time.perf_counter() - t0)
+            h.eval(backend.ALL)         # a new x invalidates the results
         print(json.dumps({
             'threads': threads, 'chunk_mb': chunk,
             'd2h_gbs': jac.nbytes / min(d2h) / 1e9,

@@ -29,7 +29,7 @@ if os.environ.get('SWEEP_SET', 'occupancy') == 'store':
 elif os.environ.get('SWEEP_SET') == 'r2':
     # round 2: balanced persistent schedule (waves = 1, 2) against one tile
     # per CTA (waves = 8), tile size x launch bounds
-    for tile, mbs in ((128, (None, 8)), (64, (None,)), (256, (None, 4))):
+    for tile, mbs in ((128, (None, 8)), (64, (None, 16)), (256, (None, 4))):
         for mb in mbs:
             VARIANTS.append(dict(tile=tile, pass_budget=6, min_blocks=mb))
 else:       # resident CTAs per SM: launch bounds x single staging buffer
@@ -39,7 +39,7 @@ else:       # resident CTAs per SM: launch bounds x single staging buffer
             VARIANTS.append(dict(tile=tile, pass_budget=6, min_blocks=mb))
 SINGLE = [int(v) for v in os.environ.get('SWEEP_SINGLE_BUF', '1,0').split(',')]
 WAVES = [int(w) for w in os.environ.get('SWEEP_WAVES', '4,8').split(',')]
-TAILS = [int(w) for w in os.environ.get('SWEEP_TAILS', '2').split(',')]
+TAILS = [0]
 
 
 def problem():
