@@ -386,14 +386,16 @@ class Generator:
             w.append('    }')
             w.append('    __syncthreads();       // the pattern table is built')
 
-        def stage(tile_expr, buf_expr):
-            """cp.async of the rows of tile ``tile_expr`` into staging buffer
-            ``buf_expr``."""
+        def stage(item_expr, buf_expr):
+            """cp.async of the rows of work item ``item_expr`` into staging
+            buffer ``buf_expr``."""
             out = ['        {',
                    f'            double* const stg = smem + '
                    f'{lay["stage_off"]} + ({buf_expr}) * {lay["stage_stride"]};',
-                   f'            const long long r0 = ({tile_expr}) * {T};',
-                   '            (void)stg; (void)r0;']
+                   '            long long r0; int spw_;',
+                   f'            cfem::item_range(a, {item_expr}, r0, spw_);',
+                   f'            const int nr = spw_ * {T // 32};',
+                   '            (void)stg; (void)nr;']
             for key in sorted(lay['stor']):
                 st_ = lay['stor'][key]
                 if key[0] == 'var':
@@ -409,56 +411,59 @@ class Generator:
                     rows = f'a.fun_rows[{key[1]}]'
                 out.append(f'            cfem::stage_rows_async<{st_["core"]}, '
                            f'{st_["nrows"]}>(stg + {st_["off"]}, {src}, '
-                           f'{rows}, r0, {st_["nrows"]}, tid);')
+                           f'{rows}, r0, nr + {st_["shift"]}, tid);')
             out.append('        }')
             return out
 
         has_red = bool(mask & (F | GRAD))
-        R = max(nred, 1)
-        # the tile's partial sums are handed to warp 0 right after the last
-        # function that feeds them, i.e. BEFORE the bulk of the tile's stores
+        # the reduction runs right after the last function that feeds it, in
+        # the CTA's LAST tile, i.e. BEFORE the bulk of that tile's stores: its
+        # fence then has no store queue to drain and the serial tail of the
+        # grid-wide tree (and of the cross-GPU exchange) overlaps the stores
         red_after = max([i for i, p in enumerate(plan) if p['reds']],
                         default=-1) if has_red else -1
-        partial_call = [
-            f'    retired = cfem::tile_partial<{R}>(a, b, tile, red, smem + '
-            f'{lay["red_off"]}, tid);']
+        reduce_call = [
+            f'        if (cfem::tree_reduce<{max(nred, 1)}>(a, b, red, smem + '
+            f'{lay["red_off"]}, tid)) {{',
+            '            // this CTA retired last: it finalises (fixed '
+            'summation tree => deterministic)',
+            f'            cfem_finalize(a, {mask}u, b, tid, smem + '
+            f'{lay["red_off"]});',
+            '            if (tid == 0) a.done_count[b] = 0u;',
+            '        }']
 
-        # Tiles: tile blockIdx.x (small launches), or drawn from the ticket
-        # counter by persistent CTAs (cfem_args.cuh).  Per tile: (1) the
-        # sample-independent blocks are streamed from the pattern table --
-        # they need no input, so these stores overlap the latency of the
-        # tile's own loads; (2) wait for the loads, then prefetch the NEXT
-        # tile's inputs (cp.async) and draw the ticket after that; (3) the
-        # tile's partial sums go to warp 0; (4) the sample-dependent blocks;
-        # (5) warp 0 looks at the retirement counter.
-        w.append('    __shared__ long long s_ticket[2];')
-        w.append('    const bool dyn = a.dynamic != 0;')
-        w.append('    long long tile = blockIdx.x;')
-        w.append('    if (dyn) {')
-        w.append('        if (tid == 0) s_ticket[0] = cfem::take_ticket(a, b);')
-        w.append('        __syncthreads();')
-        w.append('        tile = s_ticket[0];')
-        w.append('    }')
-        w.append('    if (tile < a.nitems)')
-        w += stage('tile', '0')
+        # Work items (cfem_args.cuh): CTA c takes items c, c + gridDim.x, ...;
+        # the inputs of the next item are in flight (cp.async) while this one
+        # is evaluated and streamed out.  Per item: (1) the sample-independent
+        # blocks are streamed from the pattern table -- they need no input,
+        # so these stores overlap the latency of the item's own loads; (2)
+        # wait for the loads; (3) the reduction (last item only); (4) the
+        # sample-dependent blocks.
+        w.append('    const long long G = gridDim.x;')
+        w.append('    int buf = 0;')
+        w.append('    long long item = blockIdx.x;')
+        w.append('    if (item < a.nitems)')
+        w += stage('item', '0')
         w.append('    cfem::cp_async_commit();')
-        w.append('    if (tid == 0) s_ticket[1] = (dyn && tile < a.nitems) ? '
-                 'cfem::take_ticket(a, b) : a.nitems;')
-        w.append('    int buf = 0, slot = 1;')
-        w.append('    while (tile < a.nitems) {')
-        w.append(f'    const long long kw = tile * {T} + warp * 32;    // first '
-                 'sample of this warp')
-        w.append('    const int row = tid;                  // row of this '
-                 'thread in the staged tile')
-        w.append('    unsigned retired = 0u;')
-        w.append('    (void)kw; (void)row; (void)retired;')
+        w.append('    for (; item < a.nitems; item += G, buf ^= 1) {')
+        w.append('    const bool last_item = item + G >= a.nitems;')
+        w.append('    if (!last_item)')
+        w += stage('item + G', 'buf ^ 1')
+        w.append('    cfem::cp_async_commit();')
+        w.append('    long long k0; int spw;')
+        w.append('    cfem::item_range(a, item, k0, spw);')
+        w.append('    const long long kw = k0 + warp * spw;    // first sample '
+                 'of this warp')
+        w.append('    const int row = warp * spw + lane;        // row of this '
+                 'thread in the staged item')
+        w.append('    (void)kw; (void)row;')
         for p in plan:
             if not p['uniform']:
                 continue
             fi = p['fi']
             w.append('    {')
             w.append(f'        const long long left = a.fun_rows[{fi}] - kw;')
-            w.append('        const int nvalid = left >= 32 ? 32 : '
+            w.append('        const int nvalid = left >= spw ? spw : '
                      '(left > 0 ? (int)left : 0);')
             w.append('        if (nvalid > 0) {')
             for it in p['uniform']:
@@ -467,23 +472,11 @@ class Generator:
                          'nvalid);')
             w.append('        }')
             w.append('    }')
-        w.append('    cfem::cp_async_wait<0>();      // this tile has landed')
-        w.append('    __syncthreads();               // ... and the ticket '
-                 'drawn during the previous tile')
-        w.append('    const long long next = s_ticket[slot];')
-        w.append('    if (next < a.nitems)')
-        w += stage('next', 'buf ^ 1')
-        w.append('    cfem::cp_async_commit();')
-        w.append('    // the ticket after next: requested now, stored at the '
-                 'end of this tile')
-        w.append('    long long ahead = a.nitems;')
-        w.append('    if (dyn && tid == 0 && next < a.nitems) '
-                 'ahead = cfem::take_ticket(a, b);')
+        w.append('    cfem::cp_async_wait<1>();      // this item has landed')
+        w.append('    __syncthreads();')
         w.append(f'    double* const stg = smem + {lay["stage_off"]} + buf * '
                  f'{lay["stage_stride"]};')
         w.append('    (void)stg;')
-        if has_red and red_after < 0:
-            w += partial_call
         for key in sorted(lay['stor']):
             st_ = lay['stor'][key]
             w.append(f'    const double* const {st_["name"]} = stg + '
@@ -496,7 +489,7 @@ class Generator:
             def open_block():
                 w.append('    {')
                 w.append(f'        const long long left = a.fun_rows[{fi}] - kw;')
-                w.append('        const int nvalid = left >= 32 ? 32 : '
+                w.append('        const int nvalid = left >= spw ? spw : '
                          '(left > 0 ? (int)left : 0);')
                 w.append('        const bool act = lane < nvalid;')
                 w.append('        (void)act;')
@@ -517,7 +510,9 @@ class Generator:
                              f'act ? ({code}) : 0.0;')
                 close_block()
             if pi == red_after:
-                w += partial_call
+                w.append('    if (last_item) {')
+                w += reduce_call
+                w.append('    }')
             if not p['passes']:
                 continue
             open_block()
@@ -556,20 +551,14 @@ class Generator:
                                  'nvalid);')
                     w.append('            __syncwarp();')
             close_block()
-        if has_red:
-            w.append('    if (warp == 0 && cfem::tile_retire<%d>(a, b, tile, '
-                     'retired, lane)) {' % R)
-            w.append('        // this warp retired the last group: it finalises '
-                     '(fixed summation tree => deterministic)')
-            w.append(f'        cfem_finalize(a, {mask}u, b, lane);')
-            w.append('        if (lane == 0) a.done_count[b] = 0u;')
+        w.append('    if (!last_item) __syncthreads();   // staging buffer '
+                 'is refilled by the next prefetch')
+        w.append('    }   // item loop')
+        if has_red and red_after < 0:
+            # reductions without a per-sample term still go through the tree
+            w.append('    {')
+            w += reduce_call
             w.append('    }')
-        w.append('    if (tid == 0) s_ticket[slot ^ 1] = ahead;')
-        # no barrier here: the next write to this staging buffer (the
-        # prefetch of the tile after next) and to the warp-sum scratch come
-        # after the NEXT tile's barrier
-        w.append('    tile = next; buf ^= 1; slot ^= 1;')
-        w.append('    }   // tile loop')
         w.append('    // programmatic dependent launch: the parameter-only '
                  'kernel is the prerequisite grid;')
         w.append('    // nothing here reads its results, but a completed '
@@ -939,19 +928,20 @@ class Generator:
         w.append('    }')
         w.append('}')
         w.append('')
-        w.append('// Runs in the ONE warp that retired the last group of a '
-                 'problem (tid = lane).')
+        w.append('// Runs in the last CTA of a problem (all CFEM_TILE threads).')
         w.append('static __device__ __noinline__ void cfem_finalize('
                  'const cfem::KArgs& a, const unsigned mask, const long long b, '
-                 'const int tid)')
+                 'const int tid, double* scratch)')
         w.append('{')
         w.append('    const double* __restrict__ dvec = a.dvec + b * a.ndec;')
-        w.append(f'    const double* part = a.gpartials + b * a.ngroups * {nd};')
+        w.append(f'    const double* part = a.gpartials + b * a.group_stride * {nd};')
         w.append(f'    double tot[{R}];')
         w.append(f'    for (int r = 0; r < {R}; ++r) tot[r] = 0.0;')
         for di, slot in enumerate(self.dyn_slots):
-            w.append(f'    tot[{slot}] = cfem::warp_reduce_strided(part, '
-                     f'a.ngroups, {nd}, {di}, tid);')
+            w.append(f'    tot[{slot}] = cfem::reduce_tiles<CFEM_TILE>(part, '
+                     f'a.ngroups, {nd}, {di}, scratch, tid);')
+        w.append('    if (tid >= 32) return;      // warp 0 goes on; '
+                 'the sums are in thread 0')
         w.append('    if (tid == 0) {')
         for fi, f in enumerate(self.funs):
             if not f['is_objective']:
@@ -1198,35 +1188,72 @@ class Generator:
                  'g_single_buf = atoi(v) != 0;')
         w.append('    return e;')
         w.append('}')
-        w.append("""// Launch geometry (cfem_args.cuh).  A launch whose tiles all fit resident
-// CTAs (x `waves`: the hardware dispatcher refills slots in tile order) gives
-// tile blockIdx.x to CTA blockIdx.x and needs one staging buffer.  Larger
-// launches run ONE resident set of persistent CTAs that draw tiles from the
-// ticket counter, with the second staging buffer for the prefetch
-// (`waves` <= 0 forces this form; CFEM_WAVES).  `tickets` = tickets this launch
-// consumes (0 for the static form).
-static void prepare_sample(unsigned mask, int batch, int sm_count, int waves,
-                           cfem::KArgs& a, dim3& grid, size_t& smem, long long& tickets)
+        w.append("""// Work items of one launch (cfem_args.cuh).  Full tiles first; when there is
+// enough work, the last two resident sets are half and quarter tiles (graded
+// tail): the CTAs that run last -- their slots are not refilled -- are short,
+// so the grid drains in a fraction of a tile time.  `resident` = CTAs of this
+// problem that fit on the GPU at once.
+static void build_items(long long resident, int tail_levels, cfem::KArgs& a)
 {
-    int idx = 0;
-    for (int i = 0; i < kNumMasks; ++i) if (kMasks[i] == mask) idx = i;
-    a.nitems = a.ntiles;
-    a.ngroups = (a.ntiles + cfem::kReduceGroup - 1) / cfem::kReduceGroup;
-    long long gx = (long long)g_ctas_per_sm1[idx] * sm_count * (waves > 0 ? waves : 0) / batch;
-    if (g_single_buf && gx >= a.ntiles) {
-        gx = a.ntiles;
-        smem = kSmem1[idx];
-        a.dynamic = 0;
-        tickets = 0;
-    } else {
-        gx = (long long)g_ctas_per_sm[idx] * sm_count / batch;
-        if (gx < 1) gx = 1;
-        if (gx > a.ntiles) gx = a.ntiles;
-        smem = kSmem2[idx];
-        a.dynamic = 1;
-        tickets = a.ntiles + gx;
+    const long long T = CFEM_TILE, N = a.N;
+    const int min_size = 8 * (CFEM_TILE / 32);
+    int sizes[cfem::kMaxPhases];
+    int np = 1;
+    sizes[0] = CFEM_TILE;
+    while (np < cfem::kMaxPhases && np <= tail_levels && sizes[np - 1] / 2 >= min_size) {
+        sizes[np] = sizes[np - 1] / 2;
+        ++np;
     }
+    long long tail = 0;
+    for (int p = 1; p < np; ++p) tail += resident * sizes[p];
+    if (np == 1 || N < tail + 2 * resident * T) {      // not worth grading
+        a.nphase = 1;
+        a.ph_item0[0] = 0; a.ph_k0[0] = 0; a.ph_size[0] = CFEM_TILE;
+        a.nitems = (N + T - 1) / T;
+        return;
+    }
+    a.nphase = np;
+    long long item = 0, k0 = 0;
+    for (int p = 0; p < np; ++p) {
+        a.ph_item0[p] = item; a.ph_k0[p] = k0; a.ph_size[p] = sizes[p];
+        long long count = p == 0 ? (N - tail) / T : resident;
+        if (p == np - 1) count = (N - k0 + sizes[p] - 1) / sizes[p];   // the rest
+        item += count;
+        k0 += count * sizes[p];
+    }
+    a.nitems = item;
+}
+// Launch geometry: at most `waves` resident sets of CTAs per problem, CTA c
+// takes items c, c + nctas, ...  The CTA count is the same for every kernel
+// variant of the library (the smallest residency), so the fixed-order
+// reductions give the same bits whichever variant serves a callback.  When
+// every CTA has exactly one item the second staging buffer is not allocated:
+// less shared memory per CTA, more resident CTAs per SM.
+static void prepare_sample(unsigned mask, int batch, int sm_count, int waves, int tail_levels,
+                           cfem::KArgs& a, dim3& grid, size_t& smem)
+{
+    int idx = 0, per_sm1 = 1 << 30, per_sm2 = 1 << 30;
+    for (int i = 0; i < kNumMasks; ++i) {
+        if (kMasks[i] == mask) idx = i;
+        if (g_ctas_per_sm1[i] < per_sm1) per_sm1 = g_ctas_per_sm1[i];
+        if (g_ctas_per_sm[i] < per_sm2) per_sm2 = g_ctas_per_sm[i];
+    }
+    long long resident = (long long)per_sm1 * sm_count / batch;
+    if (resident < 1) resident = 1;
+    build_items(resident, tail_levels, a);
+    long long gx = resident * waves;
+    smem = kSmem1[idx];
+    if (!g_single_buf || gx < a.nitems) {       // several items per CTA: double buffering
+        resident = (long long)per_sm2 * sm_count / batch;
+        if (resident < 1) resident = 1;
+        build_items(resident, tail_levels, a);
+        gx = resident * waves;
+        smem = kSmem2[idx];
+    }
+    if (gx > a.nitems) gx = a.nitems;
+    if (gx > a.part_stride) gx = a.part_stride;     // partial-sum slots (cfem_create)
     a.nctas = gx;
+    a.ngroups = (gx + cfem::kReduceGroup - 1) / cfem::kReduceGroup;
     grid = dim3((unsigned)gx, (unsigned)batch);
 }""")
         w.append('// overlap_prev: programmatic stream serialisation -- the kernel '
@@ -1235,14 +1262,12 @@ static void prepare_sample(unsigned mask, int batch, int sm_count, int waves,
                  'no data dependence)')
         w.append('// is still running.')
         w.append('static cudaError_t launch_sample(unsigned mask, int batch, '
-                 'int sm_count, int waves, bool overlap_prev, '
-                 'cudaStream_t s, cfem::KArgs a, long long* tickets)')
+                 'int sm_count, int waves, int tail_levels, bool overlap_prev, '
+                 'cudaStream_t s, cfem::KArgs a)')
         w.append('{')
         w.append('    cudaLaunchConfig_t cfg = {};')
         w.append('    size_t smem = 0;')
-        w.append('    long long used = 0;')
-        w.append('    prepare_sample(mask, batch, sm_count, waves, a, cfg.gridDim, smem, used);')
-        w.append('    if (tickets) *tickets = used;')
+        w.append('    prepare_sample(mask, batch, sm_count, waves, tail_levels, a, cfg.gridDim, smem);')
         w.append('    cfg.dynamicSmemBytes = smem;')
         w.append('    cfg.blockDim = dim3(CFEM_TILE);')
         w.append('    cfg.stream = s;')

@@ -8,6 +8,7 @@
 namespace cfem {
 
 constexpr int kMaxPeers = 16;
+constexpr int kMaxPhases = 4;
 
 template <int N> struct AtLeastOne { static constexpr int value = N > 0 ? N : 1; };
 
@@ -28,24 +29,28 @@ struct KArgs {
     double* g;
     double* jac;
     double* hess;
-    double* partials;       // [batch][ntiles][nreduce]: one partial sum per TILE
+    double* partials;       // [batch][part_stride][nreduce]
     // two-level deterministic reduction tree (all counters zero between launches)
-    long long     nctas;        // CTAs per problem of this launch (<= ntiles)
-    // Work items = tiles of CFEM_TILE samples.  Small launches (every tile fits
-    // a resident CTA) give tile blockIdx.x to CTA blockIdx.x.  Large launches
-    // run ONE resident set of persistent CTAs that draw tiles from a ticket
-    // counter (dynamic = 1): SMs progress at different rates under memory
-    // contention, a static partition would wait for the slowest one.  The
-    // counter is never reset: a launch consumes exactly nitems + nctas tickets
-    // (every CTA stops at its first ticket >= nitems), the host advances
-    // ticket_base by that much.
-    long long           nitems;
-    int                 dynamic;
-    unsigned long long  ticket_base;
-    unsigned long long* ticket;         // [batch]
-    long long     ngroups;      // ceil(ntiles / kReduceGroup)
-    double*       gpartials;    // [batch][ngroups][nreduce]
-    unsigned int* group_count;  // [batch][ngroups] tiles retired per group
+    long long     nctas;        // CTAs per problem of this launch (<= part_stride)
+    long long     part_stride;  // partial-sum slots per problem: partials [batch][part_stride][nreduce]
+    long long     group_stride; // ceil(part_stride / kReduceGroup): gpartials / group_count rows per problem
+    // Work items: item i covers samples [k0, k0 + size), size a multiple of
+    // 8 * warps per CTA.  The items come in up to kMaxPhases phases of
+    // decreasing size -- full tiles of CFEM_TILE samples first, then one
+    // resident set of half tiles, then quarter tiles ... (cfem_host: graded
+    // tail) -- so that the CTAs of the LAST resident set, whose slots are not
+    // refilled, are short.  (Measured on B200: the extra CTAs cost more than
+    // the shorter drain saves, so the host side builds a single phase unless
+    // CFEM_TAIL_LEVELS asks for more -- profiles/r02_experiments.)
+    // CTA c takes items c, c + nctas, ...
+    long long     nitems;
+    int           nphase;
+    long long     ph_item0[kMaxPhases];     // first item of the phase
+    long long     ph_k0[kMaxPhases];        // first sample of the phase
+    int           ph_size[kMaxPhases];      // samples per item
+    long long     ngroups;      // ceil(nctas / kReduceGroup)
+    double*       gpartials;    // [batch][group_stride][nreduce]
+    unsigned int* group_count;  // [batch][group_stride] CTAs retired per group
     unsigned int* done_count;   // [batch] groups retired per problem
     // fused cross-GPU reduction over peer memory (time-sharded runs)
     int                 peer_rank, peer_world;      // world <= 1: disabled

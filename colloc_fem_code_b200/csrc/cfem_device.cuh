@@ -17,9 +17,8 @@
 //                  lanes park their C values in the conflict-free Skew layout,
 //                  then the warp streams the 32*C contiguous doubles of the
 //                  block to HBM with unit-stride, full-sector stores;
-//   tile_partial / deterministic reduction of the per-thread objective /
-//   tile_retire    parameter-gradient partial sums: per tile, per group of
-//                  tiles, per problem -- independent of which CTA ran which tile.
+//   block_reduce   deterministic warp-shuffle + shared-memory tree reduction of
+//                  the per-thread objective / parameter-gradient partial sums.
 //
 // Reference being replaced: the NumPy broadcast evaluation of
 // /root/reference/symfem.py:50-65 (one temporary array per structural nonzero).
@@ -140,6 +139,18 @@ __device__ __forceinline__ void stage_rows_async(double* __restrict__ dst,
     }
 }
 
+// Work item -> first sample and samples per warp (cfem_args.cuh).
+__device__ __forceinline__ void item_range(const KArgs& a, long long item,
+                                           long long& k0, int& spw)
+{
+    int p = 0;
+#pragma unroll
+    for (int q = 1; q < kMaxPhases; ++q)
+        if (q < a.nphase && item >= a.ph_item0[q]) p = q;
+    k0 = a.ph_k0[p] + (item - a.ph_item0[p]) * a.ph_size[p];
+    spw = a.ph_size[p] / kWarpsPerCta;
+}
+
 // ---------------------------------------------------------------------------
 // per-warp output transposition
 // ---------------------------------------------------------------------------
@@ -234,127 +245,110 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// Named barrier 1 as a producer / consumer hand-off inside a CTA: warps that
-// only PRODUCE (their warp sums in shared memory) arrive and go on, warp 0
-// waits for all CFEM_TILE threads.
-__device__ __forceinline__ void bar_arrive1()
-{
-    asm volatile("bar.arrive 1, %0;" :: "n"(CFEM_TILE) : "memory");
-}
-__device__ __forceinline__ void bar_sync1()
-{
-    asm volatile("bar.sync 1, %0;" :: "n"(CFEM_TILE) : "memory");
-}
-
-// Next tile of a persistent CTA (cfem_args.cuh: ticket counter).
-__device__ __forceinline__ long long take_ticket(const KArgs& a, long long b)
-{
-    return (long long)(atomicAdd(a.ticket + b, 1ull) - a.ticket_base);
-}
-
-// Deterministic reduction of the per-thread partial sums `v` (objective and
-// parameter-gradient terms) over all tiles of problem `b`, whichever CTA
-// evaluates which tile:
-//   level 0  per TILE: warp shuffles, then warp 0 adds the warp sums in warp
-//            order                                       -> partials[tile]
-//   level 1  the warp that retires the last tile of a group of kReduceGroup
-//            consecutive tiles sums the group's partials (lane-strided, then
-//            a shuffle tree)                             -> gpartials[group]
-//   level 2  the warp that retires the last group sums gpartials the same way
-//            and finalises (cfem_finalize in the generated code).
-// No floating-point atomics and an association order that depends on the tile
-// numbering only: bitwise reproducible run to run, independent of the grid
-// size, of CTA scheduling and of the kernel variant.  Only warp 0 of a CTA
-// takes part beyond level 0 (no CTA-wide barrier), and tile_partial runs BEFORE
-// the tile's sample-dependent stores: its fence has no store queue to drain,
-// and the serial tail of the tree overlaps the last tiles' stores.
-//
-// tile_partial: all threads call it; returns (in lane 0 of warp 0) the number
-// of tiles of the group that had retired before this one; `v` is zeroed.
+// Deterministic CTA reduction of R per-thread values; thread 0 writes out[r].
+// `scratch` holds kWarpsPerCta * R doubles.
 template <int R>
-__device__ __forceinline__ unsigned tile_partial(const KArgs& a, long long b, long long tile,
-                                                 double (&v)[R], double* __restrict__ scratch,
-                                                 int tid)
+__device__ __forceinline__ void block_reduce_store(const double (&v)[R],
+                                                   double* __restrict__ scratch,
+                                                   double* __restrict__ out,
+                                                   int tid)
 {
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const double s = warp_sum(v[r]);
         if (lane == 0) scratch[warp * R + r] = s;
-        v[r] = 0.0;
     }
-    unsigned old = 0u;
-    if (warp != 0) {
-        __threadfence_block();
-        bar_arrive1();
-    } else {
-        bar_sync1();
-        if (lane < R) {
-            double s = 0.0;
+    __syncthreads();
+    if (tid < R) {
+        double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < kWarpsPerCta; ++w) s += scratch[w * R + lane];
-            a.partials[(b * a.ntiles + tile) * R + lane] = s;
-            __threadfence();        // publish before the retirement counter moves
-        }
-        __syncwarp();
-        if (lane == 0)
-            old = atomicAdd(a.group_count + b * a.ngroups + tile / kReduceGroup, 1u);
+        for (int w = 0; w < kWarpsPerCta; ++w) s += scratch[w * R + tid];
+        out[tid] = s;
+        __threadfence();        // publish before the retirement counter moves
     }
-    return old;
 }
 
-// Fixed-order sum of `count` values part[j * stride + slot] by ONE warp; the
-// result is valid in every lane.
-__device__ __forceinline__ double warp_reduce_strided(const double* __restrict__ part,
-                                                      long long count, int stride, int slot,
-                                                      int lane)
+// "Last block done" hand-shake: every CTA of a problem bumps the problem's
+// counter once its partial sums are globally visible; the CTA that observes
+// count == nblocks - 1 is the last one and returns true (in all its threads).
+__device__ __forceinline__ bool last_block_done(unsigned int* counter,
+                                                unsigned int nblocks, int tid)
 {
-    // 4 independent accumulators keep 4 L2 loads in flight per lane
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    long long j = lane;
-    for (; j + 96 < count; j += 128) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u)     // written by other SMs: bypass L1
-            acc[u] += __ldcg(part + (j + 32 * u) * stride + slot);
-    }
-    for (; j < count; j += 32) acc[0] += __ldcg(part + j * stride + slot);
-    double s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    return s;
+    __shared__ unsigned int s_last;
+    __syncthreads();            // the writers' fences are behind us
+    if (tid == 0) s_last = (atomicAdd(counter, 1u) == nblocks - 1u) ? 1u : 0u;
+    __syncthreads();
+    return s_last != 0u;
 }
 
-// tile_retire: warp 0 only (all 32 lanes), some time after tile_partial -- the
-// counter's answer is consumed late so that its latency is hidden.  Returns
-// true if this warp retired the last group of the problem: the caller
-// finalises.
+// Fixed-order sum over tiles of one reduction slot (one CTA per problem).
+template <int THREADS>
+__device__ __forceinline__ double reduce_tiles(const double* __restrict__ part,
+                                               long long ntiles, int nreduce,
+                                               int slot, double* scratch,
+                                               int tid)
+{
+    // 8 independent accumulators keep 8 L2 loads in flight per thread; the
+    // association order is fixed, so the sum is reproducible run to run.
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    long long t = tid;
+    for (; t + 7 * THREADS < ntiles; t += 8 * THREADS) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)     // partials were written by other SMs
+            acc[u] += __ldcg(part + (t + (long long)u * THREADS) * nreduce + slot);
+    }
+    for (; t < ntiles; t += THREADS) acc[0] += __ldcg(part + t * nreduce + slot);
+    double s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) +
+               ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    s = warp_sum(s);
+    __syncthreads();
+    if ((tid & 31) == 0) scratch[tid >> 5] = s;
+    __syncthreads();
+    double tot = 0.0;
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) tot += scratch[w];
+    }
+    return tot;     // valid in thread 0
+}
+
+// Two-level reduction of the per-thread partial sums `v` of every CTA of
+// problem `b` (objective and parameter-gradient terms):
+//   level 0  per thread over the CTA's tiles, then CTA tree (warp shuffles +
+//            shared memory)                             -> partials[cta]
+//   level 1  the last CTA of every group of kReduceGroup CTAs to retire sums
+//            the group's partials in CTA order          -> gpartials[group]
+//   level 2  the last group to retire returns true: its CTA sums gpartials in
+//            group order (cfem_finalize in the generated code).
+// No floating-point atomics and a fixed association order: bitwise
+// reproducible run to run, independent of CTA scheduling; the serial tail is
+// two short rounds of L2 loads however long the trajectory is.
 template <int R>
-__device__ __forceinline__ bool tile_retire(const KArgs& a, long long b, long long tile,
-                                            unsigned old, int lane)
+__device__ __forceinline__ bool tree_reduce(const KArgs& a, long long b,
+                                            const double (&v)[R],
+                                            double* __restrict__ scratch,
+                                            int tid)
 {
-    old = __shfl_sync(0xffffffffu, old, 0);
-    const long long g = tile / kReduceGroup;
+    const long long cta = blockIdx.x;       // one partial per (persistent) CTA
+    block_reduce_store<R>(v, scratch, a.partials + (b * a.part_stride + cta) * R, tid);
+    const long long g = cta / kReduceGroup;
     const long long first = g * kReduceGroup;
-    const long long left = a.ntiles - first;
+    const long long left = a.nctas - first;
     const unsigned in_group = left < kReduceGroup ? (unsigned)left : (unsigned)kReduceGroup;
-    if (old != in_group - 1u) return false;
-    __threadfence();            // the other tiles' partials are visible
-    const double* part = a.partials + (b * a.ntiles + first) * R;
+    unsigned int* gcount = a.group_count + b * a.group_stride + g;
+    if (!last_block_done(gcount, in_group, tid)) return false;
+    const double* part = a.partials + (b * a.part_stride + first) * R;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const double s = warp_reduce_strided(part, in_group, R, r, lane);
-        if (lane == 0) a.gpartials[(b * a.ngroups + g) * R + r] = s;
+        const double s = reduce_tiles<CFEM_TILE>(part, in_group, R, r, scratch, tid);
+        if (tid == 0) a.gpartials[(b * a.group_stride + g) * R + r] = s;
     }
-    unsigned done = 0u;
-    if (lane == 0) {
-        a.group_count[b * a.ngroups + g] = 0u;
+    if (tid == 0) {
+        *gcount = 0u;
         __threadfence();
-        done = atomicAdd(a.done_count + b, 1u);
     }
-    done = __shfl_sync(0xffffffffu, done, 0);
-    if (done != (unsigned)a.ngroups - 1u) return false;
-    __threadfence();
-    return true;
+    return last_block_done(a.done_count + b, (unsigned)a.ngroups, tid);
 }
 
 // ---------------------------------------------------------------------------

@@ -129,7 +129,8 @@ private:
 struct cfem_problem {
     int           device = 0;
     int           sm_count = 1;
-    int           waves = 1;            // launches of up to `waves` resident sets of tiles are static (tile = blockIdx.x); larger ones run persistent CTAs on a ticket counter; 0: always persistent (CFEM_WAVES)
+    int           waves = 8;            // CTAs launched <= resident CTAs x waves (B200 sweeps: the hardware CTA dispatcher balances SMs of different speed)
+    int           tail_levels = 0;      // graded tail (CFEM_TAIL_LEVELS = 1, 2: one resident set of half / quarter tiles at the end); measured slower on B200 (profiles/r02_experiments), off
     cudaStream_t  stream = nullptr;
     bool          own_stream = false;
     cudaStream_t  aux_stream = nullptr;     // parameter-only kernel, concurrent
@@ -403,7 +404,6 @@ void cfem_destroy(cfem_problem* p)
     cudaFree(p->k.done_count);
     cudaFree(p->k.group_count);
     cudaFree(p->k.gpartials);
-    cudaFree(p->k.ticket);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     for (auto& g : p->graphs) {
@@ -453,7 +453,8 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     if (!p) return cfem::fail(nullptr, CFEM_ENOMEM, "cfem_create: host allocation", cudaSuccess);
     p->device = device;
     p->sm_count = sm_count;
-    if (const char* w = getenv("CFEM_WAVES")) { p->waves = atoi(w) > 0 ? atoi(w) : 0; }
+    if (const char* w = getenv("CFEM_WAVES")) { p->waves = atoi(w) > 0 ? atoi(w) : 1; }
+    if (const char* w = getenv("CFEM_TAIL_LEVELS")) { p->tail_levels = atoi(w) >= 0 ? atoi(w) : 0; }
     if (const char* w = getenv("CFEM_PDL")) { p->use_pdl = atoi(w); }
     if (const char* w = getenv("CFEM_GRAPH")) { p->use_graph = atoi(w) != 0; }
     if (const char* w = getenv("CFEM_COPY_THREADS")) { p->copy_threads = atoi(w) > 0 ? atoi(w) : 1; }
@@ -473,8 +474,11 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     memset(&k, 0, sizeof k);
     k.N = n_samples;
     k.ntiles = (n_samples + CFEM_TILE - 1) / CFEM_TILE;
-    k.ngroups = (k.ntiles + cfem::kReduceGroup - 1) / cfem::kReduceGroup;
-    k.nitems = k.ntiles;
+    // one partial-sum slot per CTA: the graded tail adds at most ~1.25 resident
+    // sets of items (<= 32 CTAs per SM) to the tile count
+    k.part_stride = k.ntiles + 2ll * 32 * sm_count;
+    k.group_stride = (k.part_stride + cfem::kReduceGroup - 1) / cfem::kReduceGroup;
+    k.ngroups = k.group_stride;
     k.ndec = L.ndec; k.ncons = L.ncons; k.nnz_jac = L.nnz_jac; k.nnz_hess = L.nnz_hess;
     k.nreduce = gen::kNumReduce;
     k.obj_factor = 1.0;
@@ -528,13 +532,11 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     k.g = p->d_results + p->res_off[2];
     k.jac = p->d_results + p->res_off[3];
     k.hess = p->d_results + p->res_off[4];
-    CFEM_TRY(cudaMalloc(&k.partials, B * k.ntiles * gen::kNumDynReduce * D));
+    CFEM_TRY(cudaMalloc(&k.partials, B * k.part_stride * gen::kNumDynReduce * D));
     CFEM_TRY(cudaMalloc(&k.reduce, B * gen::kNumReduce * D));
-    CFEM_TRY(cudaMalloc(&k.gpartials, B * k.ngroups * gen::kNumDynReduce * D));
-    CFEM_TRY(cudaMalloc(&k.group_count, B * k.ngroups * sizeof(unsigned int)));
-    CFEM_TRY(cudaMemset(k.group_count, 0, B * k.ngroups * sizeof(unsigned int)));
-    CFEM_TRY(cudaMalloc(&k.ticket, B * sizeof(unsigned long long)));
-    CFEM_TRY(cudaMemset(k.ticket, 0, B * sizeof(unsigned long long)));
+    CFEM_TRY(cudaMalloc(&k.gpartials, B * k.group_stride * gen::kNumDynReduce * D));
+    CFEM_TRY(cudaMalloc(&k.group_count, B * k.group_stride * sizeof(unsigned int)));
+    CFEM_TRY(cudaMemset(k.group_count, 0, B * k.group_stride * sizeof(unsigned int)));
     CFEM_TRY(cudaMalloc(&k.done_count, B * sizeof(unsigned int)));
     CFEM_TRY(cudaMemset(k.done_count, 0, B * sizeof(unsigned int)));
     // structurally-zero gradient entries are written once, here
@@ -658,8 +660,7 @@ static int cfem_launch_graph(cfem_problem* p, unsigned mask, bool params)
     cfem::KArgs a1 = p->k;
     dim3 grid;
     size_t smem = 0;
-    long long tickets = 0;
-    gen::prepare_sample(mask, p->batch, p->sm_count, p->waves, a1, grid, smem, tickets);
+    gen::prepare_sample(mask, p->batch, p->sm_count, p->waves, p->tail_levels, a1, grid, smem);
     if (g.exec && g.params != params) {         // CFEM_SKIP_PARAM toggled: rebuild
         cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph);
         g = cfem_problem::StepGraph();
@@ -674,7 +675,7 @@ static int cfem_launch_graph(cfem_problem* p, unsigned mask, bool params)
             if (e == cudaSuccess) e = cudaEventRecord(p->ev_join, p->aux_stream);
         }
         if (e == cudaSuccess)
-            e = gen::launch_sample(mask, p->batch, p->sm_count, p->waves, false, p->stream, p->k, nullptr);
+            e = gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->tail_levels, false, p->stream, p->k);
         if (e == cudaSuccess && params) e = cudaStreamWaitEvent(p->stream, p->ev_join, 0);
         cudaGraph_t graph = nullptr;
         cudaError_t e2 = cudaStreamEndCapture(p->stream, &graph);
@@ -724,7 +725,6 @@ static int cfem_launch_graph(cfem_problem* p, unsigned mask, bool params)
         }
     }
     CFEM_CUDA(p, cudaGraphLaunch(g.exec, p->stream));
-    p->k.ticket_base += (unsigned long long)tickets;
     return CFEM_OK;
 }
 
@@ -746,7 +746,6 @@ int cfem_eval(cfem_problem* p, uint32_t what)
     const int slot = (int)(p->kev_count % cfem_problem::kTimingRing);
     const bool posts = p->k.peer_world > 1 && (mask & (CFEM_F | CFEM_GRAD));
     const bool pipelined = posts && p->k.peer_defer;
-    long long tickets = 0;      // drawn from the tile counter by this launch
     if (p->use_graph && !p->timing) {
         // one graph launch: both kernels as parallel nodes, no stream events
         int rc = cfem_launch_graph(p, mask, params);
@@ -762,7 +761,7 @@ int cfem_eval(cfem_problem* p, uint32_t what)
         // the native trajectory lengths, where one evaluation is 15-40 us, the
         // two launches start about 1 us earlier from two streams (fork/join).
         CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->stream, p->k));
-        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, true, p->stream, p->k, &tickets));
+        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->tail_levels, true, p->stream, p->k));
     } else {
         if (params) {
             CFEM_CUDA(p, cudaEventRecord(p->ev_fork, p->stream));
@@ -771,7 +770,7 @@ int cfem_eval(cfem_problem* p, uint32_t what)
             CFEM_CUDA(p, cudaEventRecord(p->ev_join, p->aux_stream));
         }
         if (p->timing) CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot], p->stream));
-        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, false, p->stream, p->k, &tickets));
+        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->tail_levels, false, p->stream, p->k));
         if (p->timing) {
             CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot + 1], p->stream));
             p->kev_count += 1;
@@ -779,7 +778,6 @@ int cfem_eval(cfem_problem* p, uint32_t what)
         if (params) CFEM_CUDA(p, cudaStreamWaitEvent(p->stream, p->ev_join, 0));
     }
     p->launches += params ? 2 : 1;
-    p->k.ticket_base += (unsigned long long)tickets;
     if (posts) {
         // pipelined: this launch only posted its sums; whoever consumes f / grad
         // first finishes them (cfem_join_collect); else the next launch does

@@ -225,9 +225,10 @@ class BatchFitter:
         self._backend = backend
 
     def fit(self, dec0s, dec_bounds, constr_bounds, scaling, tol=1e-8,
-            max_iter=300):
+            max_iter=300, options=None):
         """Returns ``[(decopt, info)] * B``; every argument but ``dec0s`` may
-        be a single value shared by the batch or a list of B."""
+        be a single value shared by the batch or a list of B.  ``options``:
+        numeric solver options (``mu_init``, ``bound_push`` ...)."""
         import concurrent.futures as cf
         import time
         nlp, backend = self._nlp, self._backend
@@ -244,6 +245,8 @@ class BatchFitter:
                                         per(i, constr_bounds))
             s.add_num_option('tol', tol)
             s.add_int_option('max_iter', max_iter)
+            for key, value in (options or {}).items():
+                s.add_num_option(key, value)
             s.set_scaling(*per(i, scaling))
             solvers.append(s)
             steps.append(s.solve_steps(dec0s[i]))
@@ -428,12 +431,12 @@ class ParallelBatchFitter:
         self.seconds_gpu = 0.0
 
     def _worker(self, mine, dec0s, dec_bounds, constr_bounds, scaling, tol,
-                max_iter):
+                max_iter, options=None):
         import threading
         import traceback
         try:
             self._worker_body(mine, dec0s, dec_bounds, constr_bounds, scaling,
-                              tol, max_iter)
+                              tol, max_iter, options)
         except threading.BrokenBarrierError:
             self.results.put(('error', f'worker {mine[:1]}: barrier broken '
                               'by another process'))
@@ -442,7 +445,7 @@ class ParallelBatchFitter:
             self.results.put(('error', traceback.format_exc()))
 
     def _worker_body(self, mine, dec0s, dec_bounds, constr_bounds, scaling,
-                     tol, max_iter):
+                     tol, max_iter, options=None):
         from . import nlp
         try:                        # one BLAS thread per worker process
             import threadpoolctl
@@ -461,6 +464,8 @@ class ParallelBatchFitter:
                                         per(i, constr_bounds))
             s.add_num_option('tol', tol)
             s.add_int_option('max_iter', max_iter)
+            for key, value in (options or {}).items():
+                s.add_num_option(key, value)
             s.set_scaling(*per(i, scaling))
             steps[i] = s.solve_steps(dec0s[i])
             requests[i] = next(steps[i])
@@ -503,7 +508,7 @@ class ParallelBatchFitter:
     BARRIER_TIMEOUT_S = 900.0
 
     def fit(self, dec0s, dec_bounds, constr_bounds, scaling, tol=1e-8,
-            max_iter=300):
+            max_iter=300, options=None):
         import threading
         import time
         backend = self._backend
@@ -511,7 +516,8 @@ class ParallelBatchFitter:
         slices = [list(range(w, B, W)) for w in range(W)]
         procs = [self.ctx.Process(target=self._worker,
                                   args=(sl, dec0s, dec_bounds, constr_bounds,
-                                        scaling, tol, max_iter), daemon=True)
+                                        scaling, tol, max_iter, options),
+                                  daemon=True)
                  for sl in slices]
         for pr in procs:            # fork BEFORE this process touches CUDA
             pr.start()
@@ -595,3 +601,96 @@ class ParallelBatchFitter:
             raise RuntimeError('ParallelBatchFitter: ' + (failure or '')
                                + '\n' + '\n'.join(errors))
         return out
+
+
+# ----------------------------------------------------------------------------
+# Monte-Carlo fit procedure: one attempt after the other for what did not solve
+# ----------------------------------------------------------------------------
+
+#: Attempts of the Monte-Carlo fit procedure, in order.  The reference leaves
+#: the procedure open (``estimate`` is ``pass``, mc_blackbox_cfem.py:77-78).
+#: Every attempt starts from the same predictor-consistent point
+#: (``kalman_guess``: the ``predict`` step of mc_blackbox_cfem.py:53-74 plus the
+#: filter variables); what changes is how the interior-point iteration treats
+#: the sign bounds of the square-root covariance factors, which is where the
+#: single-attempt runs of round 1 stalled (barrier parameter far ahead of the
+#: constraint violation, multipliers of the bounds blowing up):
+#:   1  IPOPT's defaults (mu_init 0.1, bound_push 1e-2);
+#:   2  a smaller initial barrier parameter;
+#:   3  a larger push away from the bounds;
+#:   4  without the sign bounds on sPp / sPc / sQ / sW (the factors are only
+#:      determined up to the sign of their columns; sRp and sR keep theirs).
+MC_ATTEMPTS = (
+    {'name': 'default', 'options': {}},
+    {'name': 'mu_init=1e-2', 'options': {'mu_init': 1e-2}},
+    {'name': 'bound_push=1e-1', 'options': {'bound_push': 1e-1}},
+    {'name': 'free factor signs', 'options': {}, 'free_factor_signs': True},
+)
+
+
+def free_factor_signs(problem, dec_bounds):
+    """Copy of ``dec_bounds`` without the lower bounds on the diagonals of
+    ``sPp`` / ``sPc`` / ``sQ`` and on ``sW_diag`` (``ml_setup``)."""
+    out = np.array(dec_bounds, dtype=float)
+    lo = problem.variables(out[0])
+    for name in ('sPp_tril', 'sPc_tril', 'sQ_tril', 'sW_diag'):
+        if name in lo:
+            lo[name][...] = -np.inf
+    return out
+
+
+def solved(info):
+    return info is not None and str(info['status']).startswith('solved')
+
+
+def fit_with_retries(make_fitter, problems, dec0s, dec_bounds, constr_bounds,
+                     scaling, tol=1e-6, max_iter=400, attempts=MC_ATTEMPTS,
+                     log=None):
+    """Run ``attempts`` one after the other on the problems that have not
+    solved yet; every attempt is ONE batch (``make_fitter(subset)`` returns a
+    ``BatchFitter`` / ``ParallelBatchFitter`` for a list of problems).
+
+    Returns ``(results, report)``: ``results[i] = (decopt, info)`` of the
+    attempt that solved problem i (or of the last one), ``info['attempt']`` its
+    index; ``report`` lists per attempt the problems tried / solved, the wall
+    time, the batched launch rounds and the GPU callback seconds.
+    """
+    import time
+    n = len(problems)
+    results = [None] * n
+    todo = list(range(n))
+    report = []
+    for k, att in enumerate(attempts):
+        if not todo:
+            break
+        sub = [problems[i] for i in todo]
+        bounds = dec_bounds
+        if att.get('free_factor_signs'):
+            bounds = free_factor_signs(sub[0], dec_bounds)
+        fitter = make_fitter(sub)
+        t0 = time.perf_counter()
+        try:
+            out = fitter.fit([dec0s[i] for i in todo], bounds, constr_bounds,
+                             scaling, tol=tol, max_iter=max_iter,
+                             options=att.get('options'))
+        finally:
+            close = getattr(fitter, 'close', None)
+            if close:
+                close()
+        wall = time.perf_counter() - t0
+        still = []
+        for i, res in zip(todo, out):
+            res[1]['attempt'] = k
+            if solved(res[1]) or results[i] is None or k == len(attempts) - 1:
+                results[i] = res
+            if not solved(res[1]):
+                still.append(i)
+        rec = {'attempt': att['name'], 'tried': len(todo),
+               'solved': len(todo) - len(still), 'wall_s': wall,
+               'launch_rounds': getattr(fitter, 'launches', None),
+               'seconds_gpu_callbacks': getattr(fitter, 'seconds_gpu', None)}
+        report.append(rec)
+        if log:
+            log(rec)
+        todo = still
+    return results, report

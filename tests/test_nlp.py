@@ -214,3 +214,46 @@ def test_batch_needs_one_obj_scale():
     assert fit._common_obj_scale([-1.0, -1.0]) == -1.0
     with pytest.raises(ValueError):
         fit._common_obj_scale([-1.0, 1.0])
+
+
+def test_fit_with_retries_only_retries_what_failed():
+    """fit.fit_with_retries: every attempt is one batch of the problems that
+    have not solved yet; the result keeps the attempt that solved it."""
+    from colloc_fem_code_b200 import fit
+    calls = []
+
+    class FakeFitter:
+        launches, seconds_gpu = 7, 0.5
+
+        def __init__(self, sub):
+            self.sub = sub
+
+        def fit(self, dec0s, dec_bounds, constr_bounds, scaling, tol,
+                max_iter, options):
+            calls.append(([p['id'] for p in self.sub], dict(options or {}),
+                          float(dec_bounds[0][0])))
+            out = []
+            for p in self.sub:
+                ok = p['solves_at'] <= len(calls) - 1
+                out.append((np.full(2, float(p['id'])),
+                            {'status': 'solved' if ok else 'max_iter'}))
+            return out
+
+        def close(self):
+            pass
+
+    class P(dict):
+        def variables(self, vec):
+            return {'sQ_tril': vec[:1], 'other': vec[1:]}
+
+    problems = [P(id=0, solves_at=0), P(id=1, solves_at=3),
+                P(id=2, solves_at=1), P(id=3, solves_at=9)]
+    bounds = np.array([[0.0, -1.0], [np.inf, np.inf]])
+    res, report = fit.fit_with_retries(FakeFitter, problems, [None] * 4,
+                                       bounds, None, None)
+    assert [c[0] for c in calls] == [[0, 1, 2, 3], [1, 2, 3], [1, 3], [1, 3]]
+    assert calls[1][1] == {'mu_init': 1e-2} and calls[3][2] == -np.inf
+    assert [r[1]['attempt'] for r in res] == [0, 3, 1, 3]
+    assert [fit.solved(r[1]) for r in res] == [True, True, True, False]
+    assert [r['solved'] for r in report] == [1, 1, 0, 1]
+    assert bounds[0][0] == 0.0              # the caller's bounds are untouched
