@@ -573,6 +573,11 @@ def run_e2e(args, torch, dist, backend, sharding, problem, ev, h, rank, world,
 
         def e2e_step(i):
             host.dvec[0] = ldvec[0] + 1e-12 * i      # a new x every step
+            if world == 1:
+                # x up, f|grad|g|Jacobian kernels and values down; lambda up
+                # and the Hessian group beside them (cfem_eval_callback_set)
+                host.callback_set(sigma)
+                return
             host.upload(sigma)           # one H2D copy: [x | lambda]
             h.eval(backend.ALL)
             if reduce_mode == 'nccl':
@@ -599,7 +604,12 @@ def run_e2e(args, torch, dist, backend, sharding, problem, ev, h, rank, world,
         e2e_ms = float(e2e_ms.item())
         e2e_h2d = int(8 * (h.ndec + h.ncons))
         e2e_d2h = int(8 * (1 + h.ndec + h.ncons + h.nnz_jac + h.nnz_hess))
-        e2e_note = ('pinned host [dvec | lambda] -> one H2D copy -> fused '
+        e2e_note = ('pinned host [dvec | lambda] -> H2D -> fused kernels -> '
+                    'D2H of [f | grad | g | Jacobian | Hessian values] (per '
+                    'rank), one C-ABI call per set '
+                    '(cfem_eval_callback_set: lambda goes up while the first '
+                    'results come down); CUDA events' if world == 1 else
+                    'pinned host [dvec | lambda] -> one H2D copy -> fused '
                     'kernels -> one D2H copy of [f | grad | g | Jacobian | '
                     'Hessian values] (per rank); CUDA events')
     else:

@@ -79,6 +79,9 @@ ABI = {
     'cfem_fetch_results_async': (ctypes.c_int, [ctypes.c_void_p,
                                                 ctypes.c_uint32,
                                                 ctypes.c_void_p]),
+    'cfem_eval_callback_set': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double,
+                                              ctypes.c_void_p,
+                                              ctypes.c_void_p]),
     'cfem_upload_pieces': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32,
                                           ctypes.c_void_p, ctypes.c_int32,
                                           ctypes.c_void_p, ctypes.c_void_p,
@@ -402,6 +405,13 @@ class Handle:
         self._check(self.lib.cfem_fetch_results_async(
             self._ptr, int(which), host_block.ctypes.data))
 
+    def eval_callback_set(self, obj_factor, host_inputs, host_results):
+        """One full callback set between page-locked host blocks, H2D of the
+        multipliers overlapped with the D2H of the first results."""
+        self._check(self.lib.cfem_eval_callback_set(
+            self._ptr, float(obj_factor), host_inputs.ctypes.data,
+            host_results.ctypes.data))
+
     @staticmethod
     def _piece_arrays(pieces):
         arr = np.ascontiguousarray(pieces, dtype=np.int64).reshape(-1, 3)
@@ -561,6 +571,11 @@ class HostBuffers:
 
     def fetch_all(self):
         self.fetch(ALL)
+
+    def callback_set(self, obj_factor):
+        """``upload`` + ``eval(ALL)`` + ``fetch_all`` with the two directions
+        of the bus overlapped (``cfem_eval_callback_set``)."""
+        self.handle.eval_callback_set(obj_factor, self.inputs, self.results)
 
     def close(self):
         self.dvec = self.lam = self.inputs = self.results = None

@@ -134,6 +134,8 @@ struct cfem_problem {
     cudaStream_t  stream = nullptr;
     bool          own_stream = false;
     cudaStream_t  aux_stream = nullptr;     // parameter-only kernel, concurrent
+    cudaStream_t  io_stream = nullptr;      // second half of cfem_eval_callback_set
+    cudaEvent_t   ev_x = nullptr, ev_io = nullptr;
     cudaEvent_t   ev_fork = nullptr, ev_join = nullptr;
     // pipelined cross-GPU reduction: the sums of the latest posting launch are
     // finished on demand (cfem_peer_collect_kernel) before f / grad are consumed
@@ -411,6 +413,9 @@ void cfem_destroy(cfem_problem* p)
         if (g.graph) cudaGraphDestroy(g.graph);
     }
     if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
+    if (p->io_stream) cudaStreamDestroy(p->io_stream);
+    if (p->ev_x) cudaEventDestroy(p->ev_x);
+    if (p->ev_io) cudaEventDestroy(p->ev_io);
     cudaFree(p->k.reduce);
     cudaFree(p->flush_buf);
     delete p->pool;
@@ -884,6 +889,63 @@ int cfem_fetch_results_async(cfem_problem* p, uint32_t which, double* host_resul
     if (hi > lo)
         CFEM_CUDA(p, cudaMemcpyAsync(host_results + lo, p->d_results + lo, (size_t)(hi - lo) * sizeof(double),
                                      cudaMemcpyDeviceToHost, p->stream));
+    return CFEM_OK;
+}
+
+// A whole callback set with both directions of the bus busy: the second group
+// (lambda up, Hessian kernels, Hessian values down) runs on its own stream
+// beside the first one (x up, f | grad | g | Jacobian kernels, their values
+// down).  The two kernel groups write disjoint outputs and only the first one
+// uses the reduction scratch.
+int cfem_eval_callback_set(cfem_problem* p, double obj_factor, const double* host_inputs,
+                           double* host_results)
+{
+    if (!p || !host_inputs || !host_results) return CFEM_EINVAL;
+    if (p->k.peer_world > 1 || p->timing)
+        return cfem::fail(p, CFEM_ESTATE, "cfem_eval_callback_set: single-GPU handles without kernel timing only", cudaSuccess);
+    CFEM_CUDA(p, cudaSetDevice(p->device));
+    if (!p->io_stream) {
+        CFEM_CUDA(p, cudaStreamCreateWithFlags(&p->io_stream, cudaStreamNonBlocking));
+        CFEM_CUDA(p, cudaEventCreateWithFlags(&p->ev_x, cudaEventDisableTiming));
+        CFEM_CUDA(p, cudaEventCreateWithFlags(&p->ev_io, cudaEventDisableTiming));
+    }
+    const size_t D = sizeof(double);
+    const long long B = p->batch;
+    cudaStream_t main_stream = p->stream;
+    // ---- group 1 on the handle's stream
+    CFEM_CUDA(p, cudaMemcpyAsync(p->d_inputs + p->in_off[0], host_inputs + p->in_off[0],
+                                 (size_t)(B * p->k.ndec) * D, cudaMemcpyHostToDevice, main_stream));
+    CFEM_CUDA(p, cudaEventRecord(p->ev_x, main_stream));
+    p->k.dvec = p->d_dvec; p->have_dvec = true; p->valid = 0;
+    // ---- lambda goes up beside it
+    if (p->k.ncons > 0)
+        CFEM_CUDA(p, cudaMemcpyAsync(p->d_inputs + p->in_off[1], host_inputs + p->in_off[1],
+                                     (size_t)(B * p->k.ncons) * D, cudaMemcpyHostToDevice, p->io_stream));
+    p->k.lam = p->d_lam; p->k.obj_factor = obj_factor; p->have_lam = true;
+    { int rc = cfem_eval(p, CFEM_F | CFEM_GRAD | CFEM_G | CFEM_JAC); if (rc) return rc; }
+    {
+        const long long lo = p->res_off[0], hi = p->res_off[3] + p->res_len[3];
+        CFEM_CUDA(p, cudaMemcpyAsync(host_results + lo, p->d_results + lo, (size_t)(hi - lo) * D,
+                                     cudaMemcpyDeviceToHost, main_stream));
+    }
+    // ---- group 2 on the second stream: needs x on the device, nothing else
+    CFEM_CUDA(p, cudaStreamWaitEvent(p->io_stream, p->ev_x, 0));
+    const int pdl = p->use_pdl;
+    const bool graph = p->use_graph;
+    p->use_pdl = 2;             // both kernels of the group on ONE stream
+    p->use_graph = false;
+    p->stream = p->io_stream;
+    int rc = cfem_eval(p, CFEM_HESS);
+    p->stream = main_stream;
+    p->use_pdl = pdl;
+    p->use_graph = graph;
+    if (rc) return rc;
+    if (p->res_len[4] > 0)
+        CFEM_CUDA(p, cudaMemcpyAsync(host_results + p->res_off[4], p->d_results + p->res_off[4],
+                                     (size_t)p->res_len[4] * D, cudaMemcpyDeviceToHost, p->io_stream));
+    CFEM_CUDA(p, cudaEventRecord(p->ev_io, p->io_stream));
+    CFEM_CUDA(p, cudaStreamWaitEvent(main_stream, p->ev_io, 0));   // later work on the handle's stream sees both groups
+    CFEM_CUDA(p, cudaStreamSynchronize(main_stream));
     return CFEM_OK;
 }
 

@@ -147,6 +147,15 @@ int          cfem_set_inputs(cfem_problem* p, uint32_t which, double obj_factor,
                              const double* host_inputs);
 int          cfem_fetch_results_async(cfem_problem* p, uint32_t which,
                                       double* host_results);
+/* One whole callback set (eval_f .. eval_h of IpStdCInterface.h at a new x and
+ * new multipliers) between page-locked host blocks laid out as above, with
+ * the two directions of the bus overlapped: x goes up first and the kernels
+ * of f | grad | g | Jacobian start; lambda goes up on a second stream WHILE the
+ * first results come down, then the Hessian kernels and their copy follow on
+ * that stream.  Returns when everything is in host_results. */
+int          cfem_eval_callback_set(cfem_problem* p, double obj_factor,
+                                    const double* host_inputs,
+                                    double* host_results);
 /* Time-sharded problems behind ONE solver process: the decision vector, the
  * multipliers and the results live in shared page-locked host vectors in the
  * GLOBAL order; every rank moves only its own pieces, straight between that

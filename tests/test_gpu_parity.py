@@ -412,6 +412,19 @@ def test_single_copy_transfers(batch):
     buf.fetch_all()
     for n in names:
         np.testing.assert_array_equal(getattr(buf, n), np.ravel(ref[n]), n)
+    # the overlapped whole-set call: lambda goes up while the first results
+    # come down (cfem_eval_callback_set)
+    buf.dvec[:] = dvec
+    buf.lam[:] = lam
+    buf.results[:] = np.nan
+    buf.callback_set(0.75)
+    for n in names:
+        np.testing.assert_array_equal(getattr(buf, n), np.ravel(ref[n]), n)
+    buf.lam[:] = 2.0 * lam
+    buf.callback_set(1.5)
+    np.testing.assert_array_equal(buf.hess, 2.0 * np.ravel(ref['hess']))
+    np.testing.assert_array_equal(buf.jac, np.ravel(ref['jac']))
+    buf.lam[:] = lam
     # x only, partial masks: the copied range spans first..last requested
     buf.dvec[:] = dvec * 1.001
     buf.upload()
