@@ -65,6 +65,8 @@ def cpu_fit(args):
     db, cb, scaling = fit.ml_setup(p)
     info = None
     for k, att in enumerate(fit.MC_ATTEMPTS):
+        if att.get('staged'):
+            continue            # the single-stage attempts only
         bounds = fit.free_factor_signs(p, db) if att.get('free_factor_signs') \
             else db
         s = nlp.InteriorPointSolver(OracleEvaluator(o), bounds, cb)
@@ -202,8 +204,8 @@ def main():
                 'unit': 'solved fits/hour', 'cores': min(cores, k),
                 'kind': 'port',
                 'sample': f'seeds 0..{k - 1}: the same problems, starts and '
-                          'attempts with CPU-oracle callbacks, one process '
-                          'per problem',
+                          'single-stage attempts with CPU-oracle callbacks, '
+                          'one process per problem',
                 'solved': cpu_solved, 'problems': k, 'wall_s': cpu_wall,
                 'seconds_per_problem_mean': float(np.mean(
                     [c['seconds'] for c in cpu])),

@@ -620,12 +620,105 @@ class ParallelBatchFitter:
 #:   3  a larger push away from the bounds;
 #:   4  without the sign bounds on sPp / sPc / sQ / sW (the factors are only
 #:      determined up to the sign of their columns; sRp and sR keep theirs).
+#:   5  staged, as the reference's stub points to (an innovation-form problem
+#:      first, mc_blackbox_cfem.py:117-118): fit the BalancedDT problem --
+#:      InnovationDT plus the balancing constraints, which remove the
+#:      similarity-transform gauge that makes the bare InnovationDT problem
+#:      singular -- then start ML+Balanced from its solution with
+#:      Q = K Rp K' and R = Rp read off the fitted innovation form
+#:      (``staged_start``).
 MC_ATTEMPTS = (
     {'name': 'default', 'options': {}},
     {'name': 'mu_init=1e-2', 'options': {'mu_init': 1e-2}},
     {'name': 'bound_push=1e-1', 'options': {'bound_push': 1e-1}},
     {'name': 'free factor signs', 'options': {}, 'free_factor_signs': True},
+    {'name': 'staged: BalancedDT fit, then ML+Balanced from it',
+     'options': {}, 'staged': True},
 )
+
+
+def balanced_setup(problem):
+    """Bounds and scaling of a BalancedDT problem in the manner of
+    /root/reference/attas_sp_innov_bal.py and blackbox_innov_bal.py:76-96."""
+    from . import models
+    dec_bounds = np.repeat([[-np.inf], [np.inf]], problem.ndec, axis=-1)
+    lo = problem.variables(dec_bounds[0])
+    ny = problem.model.ny
+    lo['sRp_tril'][models.tril_diag(ny)] = 1e-6
+    lo['sW_diag'][...] = 0.0
+    constr_scale = np.ones(problem.ncons)
+    problem.unpack_constraints(constr_scale)['innovation'][...] = 100.0
+    dec_scale = np.ones(problem.ndec)
+    ds = problem.variables(dec_scale)
+    ds['Ln'][...] = 100.0
+    ds['sRp_tril'][...] = 100.0
+    return dec_bounds, np.zeros((2, problem.ncons)), (-1.0, dec_scale,
+                                                      constr_scale)
+
+
+def staged_start(ml_problem, bal_problem, bal_dec):
+    """Feasible start of the ML+Balanced problem from a BalancedDT solution:
+    re-balance (A, B, C), read Q = K Rp K' and R = diag(Rp) off the fitted
+    innovation form (K = Ln sRp^-1, Rp = sRp sRp'), iterate the square-root
+    Riccati recursion for them and run the predictor (``kalman_guess``)."""
+    from . import models
+    v = bal_problem.variables(np.asarray(bal_dec))
+    A, B, C, D, Ln = (np.array(v[k]) for k in ('A', 'B', 'C', 'D', 'Ln'))
+    nx = len(A)
+    sRp = models.tril_mat(v['sRp_tril'])
+    Rp = sRp @ sRp.T
+    K = Ln @ np.linalg.inv(sRp)
+    T, bal = balanced_guess(A, B, C)
+    Ti = np.linalg.inv(T)
+    Kb = Ti @ K
+    sQ = np.linalg.cholesky(Kb @ Rp @ Kb.T + 1e-6 * np.eye(nx))
+    sR = np.diag(np.sqrt(np.diag(Rp)))
+    g = kalman_guess(bal_problem.y, bal_problem.u, bal['A'], bal['B'],
+                     bal['C'], D, sQ, sR, x0=Ti @ v['x'][0])
+    g.update({k: bal[k] for k in ('sW_diag', 'ctrl_orth', 'obs_orth')})
+    g['ybias'] = np.array(v['ybias'])
+    return start_point(ml_problem, g)
+
+
+def staged_attempt(make_fitter, problems, dec0s, dec_bounds, constr_bounds,
+                   scaling, tol, max_iter):
+    """Attempt 5 of ``MC_ATTEMPTS`` for a list of ML+Balanced problems:
+    two batches, BalancedDT first.  Returns ``([(decopt, info)], fitters)``."""
+    from . import families
+    bal = [families.make_problem('balanced', p.y, p.u, p.model.nx)
+           for p in problems]
+    bal0 = []
+    for p, q, d in zip(problems, bal, dec0s):
+        have = p.variables(np.asarray(d))
+        bal0.append(start_point(q, {n: have[n] for n in q.decision}))
+    db, cb, sc = balanced_setup(bal[0])
+    f1 = make_fitter(bal)
+    try:
+        out1 = f1.fit(bal0, db, cb, sc, tol=tol, max_iter=max_iter)
+    finally:
+        if getattr(f1, 'close', None):
+            f1.close()
+    starts = []
+    for p, q, d, (x1, _) in zip(problems, bal, dec0s, out1):
+        try:
+            starts.append(staged_start(p, q, x1))
+        except (np.linalg.LinAlgError, ValueError):
+            starts.append(np.asarray(d))        # keep the original start
+    f2 = make_fitter(problems)
+    try:
+        out2 = f2.fit(starts, dec_bounds, constr_bounds, scaling, tol=tol,
+                      max_iter=max_iter)
+    finally:
+        if getattr(f2, 'close', None):
+            f2.close()
+    for (_, i1), (_, i2) in zip(out1, out2):
+        i2['stage1_status'] = i1['status']
+        i2['stage1_iterations'] = i1['iterations']
+        for key in ('iterations', 'seconds_kkt', 'callback_calls',
+                    'seconds_callbacks', 'seconds_total'):
+            if key in i1 and key in i2:
+                i2[key] = i2[key] + i1[key]
+    return out2, (f1, f2)
 
 
 def free_factor_signs(problem, dec_bounds):
@@ -667,16 +760,23 @@ def fit_with_retries(make_fitter, problems, dec0s, dec_bounds, constr_bounds,
         bounds = dec_bounds
         if att.get('free_factor_signs'):
             bounds = free_factor_signs(sub[0], dec_bounds)
-        fitter = make_fitter(sub)
         t0 = time.perf_counter()
-        try:
-            out = fitter.fit([dec0s[i] for i in todo], bounds, constr_bounds,
-                             scaling, tol=tol, max_iter=max_iter,
-                             options=att.get('options'))
-        finally:
-            close = getattr(fitter, 'close', None)
-            if close:
-                close()
+        if att.get('staged'):
+            out, fitters = staged_attempt(
+                make_fitter, sub, [dec0s[i] for i in todo], bounds,
+                constr_bounds, scaling, tol, max_iter)
+        else:
+            fitter = make_fitter(sub)
+            fitters = (fitter,)
+            try:
+                out = fitter.fit([dec0s[i] for i in todo], bounds,
+                                 constr_bounds, scaling, tol=tol,
+                                 max_iter=max_iter,
+                                 options=att.get('options'))
+            finally:
+                close = getattr(fitter, 'close', None)
+                if close:
+                    close()
         wall = time.perf_counter() - t0
         still = []
         for i, res in zip(todo, out):
@@ -687,8 +787,10 @@ def fit_with_retries(make_fitter, problems, dec0s, dec_bounds, constr_bounds,
                 still.append(i)
         rec = {'attempt': att['name'], 'tried': len(todo),
                'solved': len(todo) - len(still), 'wall_s': wall,
-               'launch_rounds': getattr(fitter, 'launches', None),
-               'seconds_gpu_callbacks': getattr(fitter, 'seconds_gpu', None)}
+               'launch_rounds': sum(getattr(f, 'launches', 0) or 0
+                                    for f in fitters),
+               'seconds_gpu_callbacks': sum(getattr(f, 'seconds_gpu', 0.0)
+                                            or 0.0 for f in fitters)}
         report.append(rec)
         if log:
             log(rec)

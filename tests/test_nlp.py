@@ -250,10 +250,37 @@ def test_fit_with_retries_only_retries_what_failed():
                 P(id=2, solves_at=1), P(id=3, solves_at=9)]
     bounds = np.array([[0.0, -1.0], [np.inf, np.inf]])
     res, report = fit.fit_with_retries(FakeFitter, problems, [None] * 4,
-                                       bounds, None, None)
+                                       bounds, None, None,
+                                       attempts=fit.MC_ATTEMPTS[:4])
     assert [c[0] for c in calls] == [[0, 1, 2, 3], [1, 2, 3], [1, 3], [1, 3]]
     assert calls[1][1] == {'mu_init': 1e-2} and calls[3][2] == -np.inf
     assert [r[1]['attempt'] for r in res] == [0, 3, 1, 3]
     assert [fit.solved(r[1]) for r in res] == [True, True, True, False]
     assert [r['solved'] for r in report] == [1, 1, 0, 1]
     assert bounds[0][0] == 0.0              # the caller's bounds are untouched
+
+
+def test_staged_start_is_feasible_for_the_ml_problem():
+    """fit.staged_start: from a point of the BalancedDT problem (here: the
+    predictor run of a balanced model) to a start of ML+Balanced that satisfies
+    every constraint of that problem (oracle evaluation)."""
+    from colloc_fem_code_b200 import fit, synthetic
+    nx, nu, ny, N = 3, 2, 2, 120
+    exp = synthetic.experiment(5, N, nx, nu, ny)
+    y, u = exp['y'], exp['u']
+    T, bal = fit.balanced_guess(exp['A'], exp['B'], exp['C'])
+    g = fit.kalman_guess(y, u, bal['A'], bal['B'], bal['C'], exp['D'],
+                         0.05 * np.eye(nx), 0.2 * np.eye(ny))
+    g.update({k: bal[k] for k in ('sW_diag', 'ctrl_orth', 'obs_orth')})
+    pb = families.make_problem('balanced', y, u, nx)
+    pm = families.make_problem('ml_balanced', y, u, nx)
+    bal_dec = fit.start_point(pb, g)
+    ob = ref_models.make_problem('balanced', y, u, nx)
+    assert np.max(np.abs(ob.constr(bal_dec))) < 1e-9
+    dec0 = fit.staged_start(pm, pb, bal_dec)
+    om = ref_models.make_problem('ml_balanced', y, u, nx)
+    assert np.max(np.abs(om.constr(dec0))) < 1e-8
+    db, cb, _ = fit.ml_setup(pm)
+    assert np.all(dec0 >= db[0]) and np.all(dec0 <= db[1])
+    dbb, cbb, scb = fit.balanced_setup(pb)
+    assert dbb.shape == (2, pb.ndec) and np.all(bal_dec >= dbb[0])
