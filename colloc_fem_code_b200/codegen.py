@@ -356,6 +356,17 @@ class Generator:
         w.append('    const int tid = threadIdx.x, lane = tid & 31, '
                  'warp = tid >> 5;')
         w.append('    const long long b = blockIdx.y;')
+        if mask & (F | GRAD):
+            w.append('    if (a.finaliser && (long long)blockIdx.x == a.nctas) {')
+            w.append('        // no tile: finalise the sums and exchange them '
+                     'with the peer GPUs beside the last tiles')
+            w.append('        cfem::wait_groups_done(a, b, tid);')
+            w.append(f'        cfem_finalize(a, {mask}u, b, tid, smem + '
+                     f'{lay["red_off"]});')
+            w.append('        if (tid == 0) a.done_count[b] = 0u;')
+            w.append('        asm volatile("griddepcontrol.wait;" ::: "memory");')
+            w.append('        return;')
+            w.append('    }')
         w.append('    const double* __restrict__ dvec = a.dvec + b * a.ndec;')
         w.append('    double* const sp = smem;')
         w.append(f'    double* const wb = smem + {lay["wbuf_off"]} + warp * '
@@ -424,7 +435,7 @@ class Generator:
                         default=-1) if has_red else -1
         reduce_call = [
             f'        if (cfem::tree_reduce<{max(nred, 1)}>(a, b, red, smem + '
-            f'{lay["red_off"]}, tid)) {{',
+            f'{lay["red_off"]}, tid) && !a.finaliser) {{',
             '            // this CTA retired last: it finalises (fixed '
             'summation tree => deterministic)',
             f'            cfem_finalize(a, {mask}u, b, tid, smem + '
@@ -1161,6 +1172,8 @@ class Generator:
                  '// with the single-buffer shared-memory size')
         w.append('static bool g_single_buf = true;      // CFEM_SINGLE_BUF=0: '
                  'always both staging buffers')
+        w.append('static bool g_finaliser = true;       // CFEM_FINALISER=0: the '
+                 'last tile CTA finalises (time-sharded runs)')
         w.append('static const size_t kSmem2[] = {'
                  + ', '.join(f'kSmemBytes_m{m}' for m in self.masks) + '};')
         w.append('static const size_t kSmem1[] = {'
@@ -1186,6 +1199,8 @@ class Generator:
             w.append(f'    if (g_ctas_per_sm1[{i}] < 1) g_ctas_per_sm1[{i}] = 1;')
         w.append('    if (const char* v = getenv("CFEM_SINGLE_BUF")) '
                  'g_single_buf = atoi(v) != 0;')
+        w.append('    if (const char* v = getenv("CFEM_FINALISER")) '
+                 'g_finaliser = atoi(v) != 0;')
         w.append('    return e;')
         w.append('}')
         w.append("""// Work items of one launch (cfem_args.cuh).  Full tiles first; when there is
@@ -1254,7 +1269,8 @@ static void prepare_sample(unsigned mask, int batch, int sm_count, int waves, in
     if (gx > a.part_stride) gx = a.part_stride;     // partial-sum slots (cfem_create)
     a.nctas = gx;
     a.ngroups = (gx + cfem::kReduceGroup - 1) / cfem::kReduceGroup;
-    grid = dim3((unsigned)gx, (unsigned)batch);
+    a.finaliser = (a.peer_world > 1 && (mask & 3u) && g_finaliser) ? 1 : 0;
+    grid = dim3((unsigned)(gx + a.finaliser), (unsigned)batch);
 }""")
         w.append('// overlap_prev: programmatic stream serialisation -- the kernel '
                  'may start while the')

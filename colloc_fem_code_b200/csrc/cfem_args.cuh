@@ -31,7 +31,11 @@ struct KArgs {
     double* hess;
     double* partials;       // [batch][part_stride][nreduce]
     // two-level deterministic reduction tree (all counters zero between launches)
-    long long     nctas;        // CTAs per problem of this launch (<= part_stride)
+    long long     nctas;        // tile CTAs per problem of this launch (<= part_stride)
+    // Time-sharded runs launch ONE more CTA per problem (blockIdx.x == nctas) that has no tile: it waits
+    // for the last group of the reduction tree, finalises and runs the cross-GPU exchange, so that no
+    // tile CTA carries the NVLink round trip in front of its stores.
+    int           finaliser;
     long long     part_stride;  // partial-sum slots per problem: partials [batch][part_stride][nreduce]
     long long     group_stride; // ceil(part_stride / kReduceGroup): gpartials / group_count rows per problem
     // Work items: item i covers samples [k0, k0 + size), size a multiple of

@@ -351,6 +351,27 @@ __device__ __forceinline__ bool tree_reduce(const KArgs& a, long long b,
     return last_block_done(a.done_count + b, (unsigned)a.ngroups, tid);
 }
 
+// The finaliser CTA of a time-sharded launch (KArgs::finaliser): wait until
+// all `ngroups` groups of problem `b` have retired.  It is the LAST CTA of the
+// grid, so every tile CTA has been dispatched before it and the wait cannot
+// starve them; the spin is bounded all the same (a bug must not hang the GPU).
+__device__ __forceinline__ void wait_groups_done(const KArgs& a, long long b, int tid)
+{
+    if (tid == 0) {
+        const volatile unsigned int* done = a.done_count + b;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*done < (unsigned)a.ngroups) {
+            __nanosleep(64);
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 2000000000ull) break;
+        }
+        __threadfence();        // the groups' partial sums are visible
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------
 // fused cross-GPU reduction (time-sharded trajectories)
 // ---------------------------------------------------------------------------
