@@ -983,8 +983,12 @@ class Generator:
             for slot, code, _ in const:
                 w.append(f'    tot[{slot}] += {rows} * ({code});')
             w += undefs
+        w.append('    // this rank\'s own sums, double-buffered by launch parity '
+                 '(the side-stream exchange kernel')
+        w.append('    // of this launch reads them while the next launch is '
+                 'already running)')
         w.append(f'    for (int r = 0; r < {R}; ++r) '
-                 f'a.reduce[b * {R} + r] = tot[r];')
+                 f'a.reduce[((a.peer_epoch & 1ull) * gridDim.y + b) * {R} + r] = tot[r];')
         w.append('    }')
         w.append('    // time-sharded run: exchange the partial sums with the peer '
                  'GPUs through NVLink-mapped')
@@ -1020,6 +1024,31 @@ class Generator:
         for i, s in enumerate(self.slots[1:], start=1):
             w.append(f'    a.grad[b * a.ndec + a.var_off[{s["var"]}] + '
                      f'{s["flat"]}] = red[b * {R} + {i}];')
+        w.append('}')
+        w.append('')
+        w.append('// Pipelined cross-GPU reduction, exchange half, on a side '
+                 'stream right after the')
+        w.append('// per-sample kernel of launch a.peer_epoch (which ran WITHOUT '
+                 'peers and left this')
+        w.append('// rank\'s sums in a.reduce): finish the previous launch, then '
+                 'post this one.  It')
+        w.append('// overlaps the next per-sample kernel, so the NVLink round '
+                 'trips and the system')
+        w.append('// fence are in nobody\'s way.')
+        w.append('__global__ void cfem_peer_exchange_kernel(const cfem::KArgs a)')
+        w.append('{')
+        w.append('    const long long b = blockIdx.x, nb = gridDim.x;')
+        w.append('    const int lane = (int)threadIdx.x;')
+        w.append(f'    double tot[{R}];')
+        w.append(f'    for (int r = 0; r < {R}; ++r) '
+                 f'tot[r] = __ldcg(a.reduce + ((a.peer_epoch & 1ull) * nb + b) * {R} + r);')
+        w.append('    if (a.peer_epoch > 1ull && a.peer_prev_mask) {')
+        w.append(f'        double prev[{R}];')
+        w.append(f'        cfem::peer_collect<{R}>(a, b, nb, a.peer_epoch - 1ull, '
+                 'prev, lane);')
+        w.append('        if (lane == 0) cfem_write_sums(a, a.peer_prev_mask, b, prev);')
+        w.append('    }')
+        w.append(f'    cfem::peer_post<{R}>(a, b, nb, tot, lane);')
         w.append('}')
         w.append('')
         w.append('// Pipelined cross-GPU reduction: waits for the posts of '
@@ -1312,6 +1341,12 @@ static void prepare_sample(unsigned mask, int batch, int sm_count, int waves, in
                  'cudaStream_t s, const cfem::KArgs& a, const double* red)')
         w.append('{')
         w.append('    cfem_apply_reduced_kernel<<<batch, 32, 0, s>>>(a, red);')
+        w.append('    return cudaGetLastError();')
+        w.append('}')
+        w.append('static cudaError_t launch_peer_exchange(int batch, '
+                 'cudaStream_t s, const cfem::KArgs& a)')
+        w.append('{')
+        w.append('    cfem_peer_exchange_kernel<<<batch, 32, 0, s>>>(a);')
         w.append('    return cudaGetLastError();')
         w.append('}')
         w.append('static cudaError_t launch_peer_collect(unsigned mask, int batch, '

@@ -135,6 +135,12 @@ struct cfem_problem {
     bool          own_stream = false;
     cudaStream_t  aux_stream = nullptr;     // parameter-only kernel, concurrent
     cudaStream_t  io_stream = nullptr;      // second half of cfem_eval_callback_set
+    // pipelined cross-GPU reduction: the exchange of launch k runs as a tiny kernel on this
+    // stream beside the per-sample kernel of launch k+1 (CFEM_SIDE_EXCHANGE=0: inside the kernel)
+    cudaStream_t  xchg_stream = nullptr;
+    cudaEvent_t   ev_k1 = nullptr, ev_xchg[2] = {nullptr, nullptr};
+    bool          xchg_used[2] = {false, false};
+    bool          side_exchange = true;
     cudaEvent_t   ev_x = nullptr, ev_io = nullptr;
     cudaEvent_t   ev_fork = nullptr, ev_join = nullptr;
     // pipelined cross-GPU reduction: the sums of the latest posting launch are
@@ -414,6 +420,9 @@ void cfem_destroy(cfem_problem* p)
     }
     if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
     if (p->io_stream) cudaStreamDestroy(p->io_stream);
+    if (p->xchg_stream) cudaStreamDestroy(p->xchg_stream);
+    if (p->ev_k1) cudaEventDestroy(p->ev_k1);
+    for (cudaEvent_t e : p->ev_xchg) if (e) cudaEventDestroy(e);
     if (p->ev_x) cudaEventDestroy(p->ev_x);
     if (p->ev_io) cudaEventDestroy(p->ev_io);
     cudaFree(p->k.reduce);
@@ -468,6 +477,7 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
         if (hw && (int)(hw / 2) < p->copy_threads) p->copy_threads = hw / 2 ? hw / 2 : 1;
     }
     if (const char* w = getenv("CFEM_COPY_CHUNK_MB")) { if (atoi(w) > 0) p->bounce_bytes = (size_t)atoi(w) << 20; }
+    if (const char* w = getenv("CFEM_SIDE_EXCHANGE")) { p->side_exchange = atoi(w) != 0; }
     if (const char* w = getenv("CFEM_SKIP_PARAM")) { p->skip_param = atoi(w) != 0; }   // measurement only
     p->N = n_samples;
     p->batch = batch;
@@ -538,7 +548,7 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     k.jac = p->d_results + p->res_off[3];
     k.hess = p->d_results + p->res_off[4];
     CFEM_TRY(cudaMalloc(&k.partials, B * k.part_stride * gen::kNumDynReduce * D));
-    CFEM_TRY(cudaMalloc(&k.reduce, B * gen::kNumReduce * D));
+    CFEM_TRY(cudaMalloc(&k.reduce, 2 * B * gen::kNumReduce * D));     // double-buffered by launch parity
     CFEM_TRY(cudaMalloc(&k.gpartials, B * k.group_stride * gen::kNumDynReduce * D));
     CFEM_TRY(cudaMalloc(&k.group_count, B * k.group_stride * sizeof(unsigned int)));
     CFEM_TRY(cudaMemset(k.group_count, 0, B * k.group_stride * sizeof(unsigned int)));
@@ -546,7 +556,7 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     CFEM_TRY(cudaMemset(k.done_count, 0, B * sizeof(unsigned int)));
     // structurally-zero gradient entries are written once, here
     CFEM_TRY(cudaMemset(k.grad, 0, B * L.ndec * D));
-    CFEM_TRY(cudaMemset(k.reduce, 0, B * gen::kNumReduce * D));
+    CFEM_TRY(cudaMemset(k.reduce, 0, 2 * B * gen::kNumReduce * D));
     CFEM_TRY(cudaMemset(k.f, 0, B * D));
     for (int i = 0; i < gen::kNumData; ++i) {
         const size_t n = B * L.data_rows[i] * gen::kData[i].core;
@@ -751,6 +761,24 @@ int cfem_eval(cfem_problem* p, uint32_t what)
     const int slot = (int)(p->kev_count % cfem_problem::kTimingRing);
     const bool posts = p->k.peer_world > 1 && (mask & (CFEM_F | CFEM_GRAD));
     const bool pipelined = posts && p->k.peer_defer;
+    // pipelined exchange on the side stream: the per-sample kernel runs without peers
+    const bool side = pipelined && p->side_exchange && !p->use_graph;
+    cfem::KArgs klocal;
+    if (side) {
+        if (!p->xchg_stream) {
+            int lo = 0, hi = 0;
+            CFEM_CUDA(p, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CFEM_CUDA(p, cudaStreamCreateWithPriority(&p->xchg_stream, cudaStreamNonBlocking, hi));
+            CFEM_CUDA(p, cudaEventCreateWithFlags(&p->ev_k1, cudaEventDisableTiming));
+            for (cudaEvent_t& e : p->ev_xchg) CFEM_CUDA(p, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        // this launch overwrites the reduce buffer the exchange of two launches ago read
+        const int par = (int)(p->k.peer_epoch & 1ull);
+        if (p->xchg_used[par]) CFEM_CUDA(p, cudaStreamWaitEvent(p->stream, p->ev_xchg[par], 0));
+        klocal = p->k;
+        klocal.peer_world = 0;
+    }
+    const cfem::KArgs& kl = side ? klocal : p->k;
     if (p->use_graph && !p->timing) {
         // one graph launch: both kernels as parallel nodes, no stream events
         int rc = cfem_launch_graph(p, mask, params);
@@ -765,17 +793,17 @@ int cfem_eval(cfem_problem* p, uint32_t what)
         // per-sample kernel is long (fewer driver calls per evaluation); at
         // the native trajectory lengths, where one evaluation is 15-40 us, the
         // two launches start about 1 us earlier from two streams (fork/join).
-        CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->stream, p->k));
-        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->tail_levels, true, p->stream, p->k));
+        CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->stream, kl));
+        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->tail_levels, true, p->stream, kl));
     } else {
         if (params) {
             CFEM_CUDA(p, cudaEventRecord(p->ev_fork, p->stream));
             CFEM_CUDA(p, cudaStreamWaitEvent(p->aux_stream, p->ev_fork, 0));
-            CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->aux_stream, p->k));
+            CFEM_CUDA(p, gen::launch_param(mask, p->batch, p->aux_stream, kl));
             CFEM_CUDA(p, cudaEventRecord(p->ev_join, p->aux_stream));
         }
         if (p->timing) CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot], p->stream));
-        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->tail_levels, false, p->stream, p->k));
+        CFEM_CUDA(p, gen::launch_sample(mask, p->batch, p->sm_count, p->waves, p->tail_levels, false, p->stream, kl));
         if (p->timing) {
             CFEM_CUDA(p, cudaEventRecord(p->kev[2 * slot + 1], p->stream));
             p->kev_count += 1;
@@ -783,6 +811,15 @@ int cfem_eval(cfem_problem* p, uint32_t what)
         if (params) CFEM_CUDA(p, cudaStreamWaitEvent(p->stream, p->ev_join, 0));
     }
     p->launches += params ? 2 : 1;
+    if (side) {
+        const int par = (int)(p->k.peer_epoch & 1ull);
+        CFEM_CUDA(p, cudaEventRecord(p->ev_k1, p->stream));
+        CFEM_CUDA(p, cudaStreamWaitEvent(p->xchg_stream, p->ev_k1, 0));
+        CFEM_CUDA(p, gen::launch_peer_exchange(p->batch, p->xchg_stream, p->k));
+        CFEM_CUDA(p, cudaEventRecord(p->ev_xchg[par], p->xchg_stream));
+        p->xchg_used[par] = true;
+        p->launches += 1;
+    }
     if (posts) {
         // pipelined: this launch only posted its sums; whoever consumes f / grad
         // first finishes them (cfem_join_collect); else the next launch does
@@ -803,6 +840,10 @@ static int cfem_join_collect(cfem_problem* p)
     if (!p->collect_pending) return CFEM_OK;
     cfem::KArgs a = p->k;
     a.peer_epoch = p->collect_epoch;
+    {   // the side-stream exchange of that launch (it posts this rank's sums) comes first
+        const int par = (int)(p->collect_epoch & 1ull);
+        if (p->xchg_used[par]) CFEM_CUDA(p, cudaStreamWaitEvent(p->stream, p->ev_xchg[par], 0));
+    }
     CFEM_CUDA(p, gen::launch_peer_collect(p->collect_mask, p->batch, p->stream, a));
     p->launches += 1;
     p->collect_pending = false;
