@@ -20,6 +20,8 @@ def _free_port():
 
 
 def _rank_main(rank, world, port, mode, out):
+    if mode == 'peer_pipelined_fused':      # exchange inside the per-sample
+        os.environ['CFEM_SIDE_EXCHANGE'] = '0'      # kernel, not beside the next
     import torch
     import torch.distributed as dist
     from colloc_fem_code_b200 import backend, families, sharding, synthetic
@@ -39,15 +41,16 @@ def _rank_main(rank, world, port, mode, out):
         torch.cuda.set_stream(stream)
         h.set_stream(stream.cuda_stream)
         if mode.startswith('peer'):
-            ev.enable_peer_reduce(pipelined=mode == 'peer_pipelined')
+            ev.enable_peer_reduce(pipelined=mode.startswith('peer_pipelined'))
         res = {}
         # several epochs of the hand-shake; the pipelined exchange runs ahead
         # of its collects (ring of 4 epochs) and is only joined by a fetch
-        reps = 11 if mode == 'peer_pipelined' else 3
+        pipelined = mode.startswith('peer_pipelined')
+        reps = 11 if pipelined else 3
         for rep in range(reps):
             ev.set_point(dvec + 1e-3 * rep, sigma, lam)
             h.eval(backend.ALL)
-            if mode == 'peer_pipelined' and rep % 4 != 3 and rep != reps - 1:
+            if pipelined and rep % 4 != 3 and rep != reps - 1:
                 continue
             if mode == 'nccl':
                 ptr = h.device_ptrs()['reduce']
@@ -98,7 +101,8 @@ def _rank_main(rank, world, port, mode, out):
 
 
 @pytest.mark.parametrize('world', [2, 4, 8])
-@pytest.mark.parametrize('mode', ['peer', 'peer_pipelined', 'nccl'])
+@pytest.mark.parametrize('mode', ['peer', 'peer_pipelined',
+                                  'peer_pipelined_fused', 'nccl'])
 def test_multi_gpu_sharded_equals_single(mode, world):
     import torch
     if torch.cuda.device_count() < world:
