@@ -59,6 +59,7 @@ if ROOT not in sys.path:
 KIND = 'ml'
 DIMS = (2, 1, 2)
 N_PER_GPU = 1_000_000
+DT = 0.05       # sample time of the continuous-time families (ZOH / noise discretisation)
 METRIC = 'nlp_callback_evals_per_s'
 UNIT = 'callback sets/s (f+grad+g+Jac+Hess, N=1e6 samples per set)'
 FLUSH_BYTES = 256 << 20
@@ -225,8 +226,8 @@ def run_reference(args, out):
     nx, nu, ny = DIMS
     N = N_PER_GPU
     exp = synthetic.experiment(0, N, nx, nu, ny)
-    o = ref_models.make_problem(KIND, exp['y'], exp['u'], nx)
-    p = families.make_problem(KIND, exp['y'], exp['u'], nx)
+    o = ref_models.make_problem(KIND, exp['y'], exp['u'], nx, dt=DT)
+    p = families.make_problem(KIND, exp['y'], exp['u'], nx, dt=DT)
     dvec, lam, sigma = synthetic.evaluation_point(p, exp)
     o.constr_jac_ind()
     o.lag_hess_ind()
@@ -304,8 +305,8 @@ def cpu_baseline():
     nx, nu, ny = DIMS
     N = N_PER_GPU
     exp = synthetic.experiment(0, N, nx, nu, ny)
-    o = ref_models.make_problem(KIND, exp['y'], exp['u'], nx)
-    p = families.make_problem(KIND, exp['y'], exp['u'], nx)
+    o = ref_models.make_problem(KIND, exp['y'], exp['u'], nx, dt=DT)
+    p = families.make_problem(KIND, exp['y'], exp['u'], nx, dt=DT)
     dvec, lam, sigma = synthetic.evaluation_point(p, exp)
     times = []
     for i in range(4):
@@ -344,7 +345,7 @@ def run_ours(args, out):
     nx, nu, ny = DIMS
     N = N_PER_GPU * world
     exp = synthetic.experiment(0, N, nx, nu, ny)
-    problem = families.make_problem(KIND, exp['y'], exp['u'], nx)
+    problem = families.make_problem(KIND, exp['y'], exp['u'], nx, dt=DT)
     dvec, lam, sigma = synthetic.evaluation_point(problem, exp)
     ev = sharding.ShardedEvaluator(problem, rank, world, device=local_rank)
     h = ev.handle

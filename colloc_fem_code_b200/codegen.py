@@ -450,7 +450,8 @@ class Generator:
         # so these stores overlap the latency of the item's own loads; (2)
         # wait for the loads; (3) the reduction (last item only); (4) the
         # sample-dependent blocks.
-        w.append('    const long long G = gridDim.x;')
+        w.append('    const long long G = a.nctas;      // tile CTAs (the grid may '
+                 'hold one more: the finaliser)')
         w.append('    int buf = 0;')
         w.append('    long long item = blockIdx.x;')
         w.append('    if (item < a.nitems)')

@@ -22,6 +22,11 @@ def _free_port():
 def _rank_main(rank, world, port, mode, out):
     if mode == 'peer_pipelined_fused':      # exchange inside the per-sample
         os.environ['CFEM_SIDE_EXCHANGE'] = '0'      # kernel, not beside the next
+    many_tiles = mode.endswith('_many_tiles')
+    if many_tiles:
+        # several tiles per (persistent) CTA: one resident set of CTAs only
+        os.environ['CFEM_WAVES'] = '1'
+        mode = mode[:-len('_many_tiles')]
     import torch
     import torch.distributed as dist
     from colloc_fem_code_b200 import backend, families, sharding, synthetic
@@ -32,6 +37,8 @@ def _rank_main(rank, world, port, mode, out):
                             device_id=torch.device('cuda', rank))
     try:
         nx, nu, ny, N = 2, 1, 2, 20001
+        if many_tiles:
+            N = 200_001 * world         # > 1 184 tiles per rank
         exp = synthetic.experiment(5, N, nx, nu, ny)
         p = families.make_problem('ml', exp['y'], exp['u'], nx)
         dvec, lam, sigma = synthetic.evaluation_point(p, exp)
@@ -102,7 +109,9 @@ def _rank_main(rank, world, port, mode, out):
 
 @pytest.mark.parametrize('world', [2, 4, 8])
 @pytest.mark.parametrize('mode', ['peer', 'peer_pipelined',
-                                  'peer_pipelined_fused', 'nccl'])
+                                  'peer_pipelined_fused', 'nccl',
+                                  'peer_many_tiles',
+                                  'peer_pipelined_many_tiles'])
 def test_multi_gpu_sharded_equals_single(mode, world):
     import torch
     if torch.cuda.device_count() < world:
