@@ -37,6 +37,10 @@ ALL = 31
 #: kernel variants that are instantiated (a request is served by the smallest
 #: superset): single callbacks, IPOPT's usual groupings and the full set.
 DEFAULT_MASKS = (F, F | GRAD, G, JAC, HESS, F | G, F | GRAD | G | JAC, ALL)
+# defaults of the two round-2 kernel options (Generator.__init__); the
+# alternatives stay selectable (CFEM_RETIRE / CFEM_EARLY_LOADS at build time)
+DEFAULT_RETIRE = 'tree'
+DEFAULT_EARLY_LOADS = 0
 
 
 def _skew_size(c, rows):
@@ -66,7 +70,8 @@ class _Item:
 
 class Generator:
     def __init__(self, structure, tile=None, pass_budget=None, masks=None,
-                 min_blocks=None, experiment=None, store=None):
+                 min_blocks=None, experiment=None, store=None, retire=None,
+                 early_loads=None):
         self.st = structure
         self.masks = tuple(masks or DEFAULT_MASKS)
         self.funs = structure.funs
@@ -88,6 +93,17 @@ class Generator:
         # tuning experiments only (tools/sweep.py): 'nostore' / 'noload'
         self.experiment = experiment
         self.store = store          # None (st.global.cs) | 'wb' | 'cg' | 'wt'
+        # retirement of the tile CTAs' partial sums: 'tree' = "last block
+        # done" tree (fence + ticket per CTA), 'flag' = self-validating slots
+        # polled by a finaliser CTA (cfem_device.cuh, "fence-free retirement")
+        self.retire = retire or os.environ.get('CFEM_RETIRE') or DEFAULT_RETIRE
+        assert self.retire in ('tree', 'flag')
+        # issue the first tile's cp.async loads BEFORE the parameters are
+        # staged and the pattern table is built (one prologue barrier)
+        if early_loads is None:
+            early_loads = int(os.environ.get('CFEM_EARLY_LOADS',
+                                             DEFAULT_EARLY_LOADS))
+        self.early_loads = bool(early_loads)
         self._reduce_slots()
 
     # ------------------------------------------------------------------
@@ -360,10 +376,12 @@ class Generator:
             w.append('    if (a.finaliser && (long long)blockIdx.x == a.nctas) {')
             w.append('        // no tile: finalise the sums and exchange them '
                      'with the peer GPUs beside the last tiles')
-            w.append('        cfem::wait_groups_done(a, b, tid);')
+            if self.retire == 'tree':
+                w.append('        cfem::wait_groups_done(a, b, tid);')
             w.append(f'        cfem_finalize(a, {mask}u, b, tid, smem + '
                      f'{lay["red_off"]});')
-            w.append('        if (tid == 0) a.done_count[b] = 0u;')
+            if self.retire == 'tree':
+                w.append('        if (tid == 0) a.done_count[b] = 0u;')
             w.append('        asm volatile("griddepcontrol.wait;" ::: "memory");')
             w.append('        return;')
             w.append('    }')
@@ -372,30 +390,6 @@ class Generator:
         w.append(f'    double* const wb = smem + {lay["wbuf_off"]} + warp * '
                  f'{lay["wbuf"]};')
         w.append('    (void)lane; (void)dvec; (void)sp; (void)wb;')
-        for v, off in sorted(lay['param_off'].items()):
-            w.append(f'    cfem::stage_contig(sp + {off}, dvec + '
-                     f'a.var_off[{v}], {self.st.vars[v]["core"]}, tid);')
-        if mask & (F | GRAD):
-            w.append(f'    double red[{max(nred, 1)}];')
-            w.append(f'    for (int r = 0; r < {max(nred, 1)}; ++r) '
-                     'red[r] = 0.0;')
-        w.append(f'    double* const pat = smem + {lay["pat_off"]};')
-        w.append('    (void)pat;')
-        if any(p['uniform'] for p in plan):
-            w.append('    __syncthreads();       // parameters are staged')
-            w.append('    if (tid == 0) {        // once per (persistent) CTA')
-            for p in plan:
-                f = self.funs[p['fi']]
-                for it in p['uniform']:
-                    defs, undefs = self._define_args(f, it.deps, 'sample', lay)
-                    w += defs
-                    for j, code in enumerate(it.codes):
-                        if it.mult:
-                            code = f'({it.mult[j]}) * ({code})'
-                        w.append(f'        pat[{it.pat_off + j}] = {code};')
-                    w += undefs
-            w.append('    }')
-            w.append('    __syncthreads();       // the pattern table is built')
 
         def stage(item_expr, buf_expr):
             """cp.async of the rows of work item ``item_expr`` into staging
@@ -442,6 +436,12 @@ class Generator:
             f'{lay["red_off"]});',
             '            if (tid == 0) a.done_count[b] = 0u;',
             '        }']
+        if self.retire == 'flag':
+            reduce_call = [
+                '        // one store per slot, no fence, no ticket: the finaliser '
+                'CTA polls the slots',
+                f'        cfem::publish_partial<{max(nred, 1)}>(a, b, red, smem + '
+                f'{lay["red_off"]}, tid);']
 
         # Work items (cfem_args.cuh): CTA c takes items c, c + gridDim.x, ...;
         # the inputs of the next item are in flight (cp.async) while this one
@@ -454,9 +454,49 @@ class Generator:
                  'hold one more: the finaliser)')
         w.append('    int buf = 0;')
         w.append('    long long item = blockIdx.x;')
-        w.append('    if (item < a.nitems)')
-        w += stage('item', '0')
-        w.append('    cfem::cp_async_commit();')
+        if self.early_loads:
+            # the tile's loads depend on nothing but the block index: they go
+            # first, the prologue below runs under their latency
+            w.append('    if (item < a.nitems)')
+            w += stage('item', '0')
+            w.append('    cfem::cp_async_commit();')
+        for v, off in sorted(lay['param_off'].items()):
+            w.append(f'    cfem::stage_contig(sp + {off}, dvec + '
+                     f'a.var_off[{v}], {self.st.vars[v]["core"]}, tid);')
+        if mask & (F | GRAD):
+            w.append(f'    double red[{max(nred, 1)}];')
+            w.append(f'    for (int r = 0; r < {max(nred, 1)}; ++r) '
+                     'red[r] = 0.0;')
+        w.append(f'    double* const pat = smem + {lay["pat_off"]};')
+        w.append('    (void)pat;')
+        if any(p['uniform'] for p in plan):
+            if self.early_loads:
+                # the pattern entries read the parameters from global memory
+                # (no dependence on the staged copy): one barrier covers both
+                w.append(f'    if (tid == {T - 32}) {{   // once per (persistent) '
+                         'CTA, beside the staging of warp 0')
+            else:
+                w.append('    __syncthreads();       // parameters are staged')
+                w.append('    if (tid == 0) {        // once per (persistent) CTA')
+            for p in plan:
+                f = self.funs[p['fi']]
+                for it in p['uniform']:
+                    defs, undefs = self._define_args(
+                        f, it.deps, 'global' if self.early_loads else 'sample',
+                        lay)
+                    w += defs
+                    for j, code in enumerate(it.codes):
+                        if it.mult:
+                            code = f'({it.mult[j]}) * ({code})'
+                        w.append(f'        pat[{it.pat_off + j}] = {code};')
+                    w += undefs
+            w.append('    }')
+            w.append('    __syncthreads();       // parameters staged, pattern '
+                     'table built')
+        if not self.early_loads:
+            w.append('    if (item < a.nitems)')
+            w += stage('item', '0')
+            w.append('    cfem::cp_async_commit();')
         w.append('    for (; item < a.nitems; item += G, buf ^= 1) {')
         w.append('    const bool last_item = item + G >= a.nitems;')
         w.append('    if (!last_item)')
@@ -946,12 +986,22 @@ class Generator:
                  'const int tid, double* scratch)')
         w.append('{')
         w.append('    const double* __restrict__ dvec = a.dvec + b * a.ndec;')
-        w.append(f'    const double* part = a.gpartials + b * a.group_stride * {nd};')
         w.append(f'    double tot[{R}];')
         w.append(f'    for (int r = 0; r < {R}; ++r) tot[r] = 0.0;')
-        for di, slot in enumerate(self.dyn_slots):
-            w.append(f'    tot[{slot}] = cfem::reduce_tiles<CFEM_TILE>(part, '
-                     f'a.ngroups, {nd}, {di}, scratch, tid);')
+        if self.retire == 'flag':
+            # a structure without per-sample reduction terms still publishes
+            # one (zero) slot per CTA: the finaliser must see every CTA
+            for di, slot in enumerate(self.dyn_slots or [None]):
+                call = (f'cfem::collect_partials(a, b, {nd}, {di}, scratch, '
+                        'tid);')
+                w.append(f'    tot[{slot}] = {call}' if slot is not None
+                         else f'    (void){call}')
+        else:
+            w.append(f'    const double* part = a.gpartials + b * '
+                     f'a.group_stride * {nd};')
+            for di, slot in enumerate(self.dyn_slots):
+                w.append(f'    tot[{slot}] = cfem::reduce_tiles<CFEM_TILE>(part, '
+                         f'a.ngroups, {nd}, {di}, scratch, tid);')
         w.append('    if (tid >= 32) return;      // warp 0 goes on; '
                  'the sums are in thread 0')
         w.append('    if (tid == 0) {')
@@ -1196,6 +1246,10 @@ class Generator:
         w.append(finalize)
         w += kernels
         w.append(f'constexpr int kNumParamEntries = {self.n_param_entries};')
+        w.append('// partial sums retire through self-validating slots and a '
+                 'finaliser CTA')
+        w.append('constexpr bool kFlagRetire = '
+                 f'{"true" if self.retire == "flag" else "false"};')
         w.append(launch_param_sig + ';    // parameter-only unit')
         w.append(f'static int g_ctas_per_sm[{len(self.masks)}];')
         w.append(f'static int g_ctas_per_sm1[{len(self.masks)}];   '
@@ -1299,7 +1353,7 @@ static void prepare_sample(unsigned mask, int batch, int sm_count, int waves, in
     if (gx > a.part_stride) gx = a.part_stride;     // partial-sum slots (cfem_create)
     a.nctas = gx;
     a.ngroups = (gx + cfem::kReduceGroup - 1) / cfem::kReduceGroup;
-    a.finaliser = (a.peer_world > 1 && (mask & 3u) && g_finaliser) ? 1 : 0;
+    a.finaliser = ((mask & 3u) && (kFlagRetire || (a.peer_world > 1 && g_finaliser))) ? 1 : 0;
     grid = dim3((unsigned)(gx + a.finaliser), (unsigned)batch);
 }""")
         w.append('// overlap_prev: programmatic stream serialisation -- the kernel '

@@ -351,6 +351,116 @@ __device__ __forceinline__ bool tree_reduce(const KArgs& a, long long b,
     return last_block_done(a.done_count + b, (unsigned)a.ngroups, tid);
 }
 
+// ---------------------------------------------------------------------------
+// fence-free retirement (generator option retire='flag')
+// ---------------------------------------------------------------------------
+// The "last block done" tree above costs every tile CTA a __threadfence (which
+// waits for the CTA's sample-independent stores, issued just before, to drain),
+// an atomic round trip and two CTA-wide barriers: 22 % of the warp-stall
+// samples of the round-2 ncu report (profiles/r02_stall_breakdown.md).  Here a
+// tile CTA only STORES its partial sums: every 8-byte slot of `partials` is its
+// own validity flag -- it holds kSlotEmpty (a NaN that no arithmetic produces;
+// computed NaNs are canonicalised before they are published) until the CTA
+// writes it, and nothing else has to be ordered with that store, so no fence,
+// no atomic and no second barrier.  One extra CTA without a tile (the
+// finaliser, the LAST CTA of the grid, so every tile CTA has been dispatched
+// before it) polls the slots with relaxed gpu-scope loads while the last tiles
+// are still running, adds them in a fixed order (thread t takes slots t,
+// t + CFEM_TILE, ... in increasing order, then the usual warp / CTA tree) and
+// re-arms every slot it has consumed for the next launch.
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+constexpr unsigned long long kSlotEmpty = 0xffffffffffffffffull;    // = cudaMemset(0xff)
+
+__device__ __forceinline__ void st_relaxed_gpu_u64(double* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const double* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Tile CTA: CTA sum of the per-thread values, published to the CTA's slots.
+template <int R>
+__device__ __forceinline__ void publish_partial(const KArgs& a, long long b,
+                                                const double (&v)[R],
+                                                double* __restrict__ scratch, int tid)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double s = warp_sum(v[r]);
+        if (lane == 0) scratch[warp * R + r] = s;
+    }
+    __syncthreads();
+    if (tid < R) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; ++w) s += scratch[w * R + tid];
+        unsigned long long bits = (unsigned long long)__double_as_longlong(s);
+        if (s != s) bits = 0x7ff8000000000000ull;       // never kSlotEmpty
+        st_relaxed_gpu_u64(a.partials + (b * a.part_stride + (long long)blockIdx.x) * R + tid, bits);
+    }
+}
+
+// Finaliser CTA: fixed-order sum of slot `r` of the `n` tile CTAs of problem
+// `b`; valid in thread 0.  Up to kPollBatch slots per thread are polled
+// together (independent loads); the spin is bounded: a CTA that never
+// publishes yields NaN sums instead of a hung GPU.
+constexpr int kPollBatch = 8;
+__device__ __forceinline__ double collect_partials(const KArgs& a, long long b, int R, int r,
+                                                   double* scratch, int tid)
+{
+    double* __restrict__ part = a.partials + b * a.part_stride * R + r;
+    const long long n = a.nctas;
+    double acc = 0.0;
+    bool ok = true;
+    const unsigned long long t0 = global_ns();
+    for (long long base = tid; base < n; base += (long long)kPollBatch * CFEM_TILE) {
+        unsigned long long bits[kPollBatch];
+        for (;;) {
+            bool all = true;
+#pragma unroll
+            for (int u = 0; u < kPollBatch; ++u) {
+                const long long i = base + (long long)u * CFEM_TILE;
+                bits[u] = i < n ? ld_relaxed_gpu_u64(part + i * R) : 0ull;
+                all = all && bits[u] != kSlotEmpty;
+            }
+            if (all) break;
+            __nanosleep(64);
+            if (global_ns() - t0 > 2000000000ull) { ok = false; break; }
+        }
+#pragma unroll
+        for (int u = 0; u < kPollBatch; ++u) {
+            const long long i = base + (long long)u * CFEM_TILE;
+            if (i < n) {
+                acc += __longlong_as_double((long long)bits[u]);
+                st_relaxed_gpu_u64(part + i * R, kSlotEmpty);      // re-arm for the next launch
+            }
+        }
+        if (!ok) break;
+    }
+    if (!ok) acc = __longlong_as_double(0x7ff8000000000000ll);
+    acc = warp_sum(acc);
+    __syncthreads();
+    if ((tid & 31) == 0) scratch[tid >> 5] = acc;
+    __syncthreads();
+    double tot = 0.0;
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; ++w) tot += scratch[w];
+    }
+    return tot;     // valid in thread 0
+}
+
 // The finaliser CTA of a time-sharded launch (KArgs::finaliser): wait until
 // all `ngroups` groups of problem `b` have retired.  It is the LAST CTA of the
 // grid, so every tile CTA has been dispatched before it and the wait cannot
@@ -423,12 +533,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
     unsigned long long v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
-}
-__device__ __forceinline__ unsigned long long global_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
 }
 
 // The hand-shake is executed by ONE WARP (all 32 lanes call these functions

@@ -548,6 +548,9 @@ int cfem_create(cfem_problem** out, int64_t n_samples, int32_t batch,
     k.jac = p->d_results + p->res_off[3];
     k.hess = p->d_results + p->res_off[4];
     CFEM_TRY(cudaMalloc(&k.partials, B * k.part_stride * gen::kNumDynReduce * D));
+    // fence-free retirement: every slot starts as cfem::kSlotEmpty (all ones)
+    if (gen::kFlagRetire)
+        CFEM_TRY(cudaMemset(k.partials, 0xff, B * k.part_stride * gen::kNumDynReduce * D));
     CFEM_TRY(cudaMalloc(&k.reduce, 2 * B * gen::kNumReduce * D));     // double-buffered by launch parity
     CFEM_TRY(cudaMalloc(&k.gpartials, B * k.group_stride * gen::kNumDynReduce * D));
     CFEM_TRY(cudaMalloc(&k.group_count, B * k.group_stride * sizeof(unsigned int)));

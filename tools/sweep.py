@@ -32,6 +32,25 @@ elif os.environ.get('SWEEP_SET') == 'r2':
     for tile, mbs in ((128, (None, 8)), (64, (None, 16)), (256, (None, 4))):
         for mb in mbs:
             VARIANTS.append(dict(tile=tile, pass_budget=6, min_blocks=mb))
+elif os.environ.get('SWEEP_SET') == 'retire':
+    # round 2, second session: retirement of the partial sums ("last block
+    # done" tree against self-validating slots + finaliser CTA) x first
+    # tile's loads before / after the prologue, then tile size, output-pass
+    # budget and forced residency on top of the fence-free form
+    for retire in ('tree', 'flag'):
+        for early in (0, 1):
+            VARIANTS.append(dict(tile=128, pass_budget=6, retire=retire,
+                                 early_loads=early))
+    if os.environ.get('SWEEP_WIDE', '1') == '1':
+        for tile in (64, 256):
+            VARIANTS.append(dict(tile=tile, pass_budget=6, retire='flag',
+                                 early_loads=1))
+        for pb in (4, 8, 12):
+            VARIANTS.append(dict(tile=128, pass_budget=pb, retire='flag',
+                                 early_loads=1))
+        for mb in (10, 12):
+            VARIANTS.append(dict(tile=128, pass_budget=6, retire='flag',
+                                 early_loads=1, min_blocks=mb))
 else:       # resident CTAs per SM: launch bounds x single staging buffer
     for tile, mbs in ((64, (None, 16, 18, 20)), (128, (None, 8, 9, 10)),
                       (256, (None, 4, 5))):
