@@ -64,3 +64,30 @@ def test_create_fails_loudly_without_a_gpu():
     p, lib = _library()
     with pytest.raises(backend.CfemError):
         p.obj(np.zeros(p.ndec))
+
+
+def test_kernel_options_generate_and_build():
+    """The two alternative forms of the per-sample kernel (fence-free
+    retirement of the partial sums, tile loads before the prologue;
+    profiles/r02_stall_breakdown.md) stay buildable and export the same ABI.
+    Their results are checked on the GPU by running the parity suite with
+    CFEM_RETIRE=flag CFEM_EARLY_LOADS=1."""
+    from colloc_fem_code_b200 import codegen
+    p = families.make_problem('innovation', np.zeros((4, 1)), np.zeros((4, 1)),
+                              1, dt=0.1)
+    base = codegen.generate(p.structure)['main']
+    assert 'tree_reduce<' in base and 'publish_partial<' not in base
+    assert 'kFlagRetire = false' in base
+    src = codegen.generate(p.structure, retire='flag', early_loads=1)['main']
+    kernels = src[src.index('// mask 1:'):]
+    assert 'publish_partial<' in kernels and 'tree_reduce<' not in kernels
+    assert 'collect_partials(' in src and 'kFlagRetire = true' in src
+    # the first tile's loads come before the parameter staging
+    k31 = kernels[kernels.index('cfem_sample_kernel_m31'):]
+    assert k31.index('stage_rows_async') < k31.index('stage_contig')
+    path = backend.build_library(p.structure,
+                                 backend.structure_label(p.structure),
+                                 retire='flag', early_loads=1)
+    dll = ctypes.CDLL(path)
+    for name in _header_symbols():
+        assert hasattr(dll, name), name
