@@ -203,3 +203,138 @@ def test_stale_variable_views():
     lob = np.full(pb.ndec, -np.inf)
     pb.variables(lob)['W_diag'][:] = 0              # blackbox_innov_bal.py:80
     assert (pb.variables(lob)['sW_diag'] == 0).all()
+
+
+HEAD_RUNNER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, 'tests'))
+sys.path.insert(0, %(ref)r)              # the script runs from the reference's directory
+import colloc_fem_code_b200.compat as compat
+compat.install()                        # the one line a maintainer adds
+from colloc_fem_code_b200 import nlp
+from oracle import ref_models
+from nlp_helpers import OracleEvaluator, attas_like_experiment
+
+# No GPU in this test: the callbacks come from the CPU oracle of the same
+# problem family (identical layouts, tests/test_host_layout.py).
+def cpu_evaluator(problem):
+    o = ref_models.make_problem(%(kind)r, problem.y, problem.u, problem.model.nx,
+                                dt=getattr(problem.model, 'dt', None))
+    assert (o.ndec, o.ncons) == (problem.ndec, problem.ncons)
+    return OracleEvaluator(o)
+nlp.GpuEvaluator = cpu_evaluator
+cap = nlp.Solver.add_int_option
+def capped(self, key, value):       # the point is to execute, not to converge
+    cap(self, key, min(value, 15) if key == 'max_iter' else value)
+nlp.Solver.add_int_option = capped
+
+N = 80
+exp = attas_like_experiment(2, N)       # every state measured, as the scripts impose (C = I)
+src = open(%(script)r).read()
+main_at = src.index("if __name__ == '__main__':")
+ns = {'__name__': 'head_script', '__file__': %(script)r}
+exec(compile(src[:main_at], %(script)r, 'exec'), ns)
+import fem, symfem
+assert symfem.__file__.startswith(%(ref)r) and fem.__file__.startswith(%(ref)r)
+ns['load_data'] = lambda: (0.05 * np.arange(N), exp['u'].copy(), exp['y'].copy(),
+                           np.zeros(2), np.ones(2), np.zeros(1), np.ones(1))
+body = 'if True:' + src[main_at + len("if __name__ == '__main__':"):]
+exec(compile(body, %(script)r + ':main', 'exec'), ns)
+p = ns['problem']
+assert p.ndec == len(ns['decopt']) and np.all(np.isfinite(ns['decopt']))
+assert ns['xopt'].shape == (N, 2) and ns['enopt'].shape == (N, 2)
+assert ns['yopt'].shape == (N, 2) and ns['sRp'].shape == (2, 2)
+assert ns['info']['iterations'] >= 1
+%(extra)s
+print('status:', ns['info']['status'], 'iterations:', ns['info']['iterations'])
+print('ok')
+'''
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, 'symfem.py')),
+                    reason='reference tree only exists in the build container')
+@pytest.mark.parametrize('script,kind,extra', [
+    ('attas_sp_innov.py', 'innovation', ''),
+    ('attas_sp_innov_bal.py', 'balanced',
+     "assert ns['W'].shape == (2, 2)"),
+    ('attas_sp_ml.py', 'ml',
+     "assert ns['Pp'].shape == (2, 2) and ns['Kn'].shape == (2, 2)"),
+    ('attas_sp_ml_zoh.py', 'ml_zoh',
+     "assert ns['Ac'].shape == (2, 2) and abs(ns['model'].dt - 0.05) < 1e-12"),
+    ('attas_sp_ml_ndisc.py', 'ndisc_zoh',
+     "assert ns['Qc'].shape == (2, 2) and ns['Bc'].shape == (2, 1)"),
+])
+def test_head_script_bodies_execute(script, kind, extra):
+    """The five current ATTAS scripts of the reference run AS WRITTEN, from the
+    first import to the last statement, on the reference's own unchanged
+    ``symfem.py`` / ``fem.py`` with ``compat.install()`` in front (initial
+    guesses, bounds, scaling, ``problem.ipopt(...)``, options, ``solve``,
+    unpacking of the optimum); only ``load_data`` is patched to synthetic
+    arrays (the flight-test files are not shipped) and the CPU oracle serves
+    the callbacks (no GPU here)."""
+    code = HEAD_RUNNER % {'root': ROOT, 'ref': REF, 'kind': kind,
+                          'script': os.path.join(REF, script), 'extra': extra}
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True,
+                         text=True, timeout=900, cwd='/tmp')
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-4000:])
+    assert out.stdout.strip().endswith('ok')
+
+
+MC_RUNNER = r'''
+import os, sys, tempfile
+import numpy as np, scipy.io
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, %(ref)r)
+import colloc_fem_code_b200.compat as compat
+compat.install()
+from colloc_fem_code_b200 import synthetic
+work = tempfile.mkdtemp()
+os.chdir(work)                          # get_model writes the generated module here
+sys.path.insert(0, work)
+edir = os.path.join(work, 'mc_experim')
+os.makedirs(edir)
+nx, nu, ny, N = 5, 3, 3, 500            # mc_data_gen.m:5-16
+scipy.io.savemat(os.path.join(edir, 'config.mat'), {'nx': nx, 'nu': nu, 'ny': ny})
+exp = synthetic.experiment(0, N, nx, nu, ny)
+scipy.io.savemat(os.path.join(edir, 'exp001.mat'), {'u': exp['u'], 'y': exp['y']})
+script = %(script)r
+src = open(script).read()
+main_at = src.index("if __name__ == '__main__':")
+ns = {'__name__': 'mc_script', '__file__': script}
+exec(compile(src[:main_at], script, 'exec'), ns)
+sys.argv = ['mc_blackbox_cfem.py', edir]
+body = 'if True:' + src[main_at + len("if __name__ == '__main__':"):]
+try:
+    exec(compile(body, script + ':main', 'exec'), ns)
+except SystemExit:
+    pass                                # mc_blackbox_cfem.py:120 stops after the first problem pair
+else:
+    raise AssertionError('the script is expected to stop at its raise SystemExit')
+name = 'GeneratedBalancedMaximumLikelihoodModel_nx5_nu3_ny3'
+assert os.path.isfile(os.path.join(work, name + '.py'))         # print_code round trip
+assert type(ns['model']).__name__ == 'GeneratedBalancedMaximumLikelihoodModel'
+assert ns['ye'].shape == (250, 3)                               # second half of the record
+ml, inn = ns['ml_prob'], ns['in_prob']
+assert (ml.ndec, ml.ncons) == (2353, 2285)                      # SURVEY appendix B
+assert (inn.ndec, inn.ncons) == (88 + 250 * 8, 250 * 8 - 5)
+assert set(inn.decision) < set(ml.decision)
+print('ok')
+'''
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, 'symfem.py')),
+                    reason='reference tree only exists in the build container')
+def test_mc_script_executes():
+    """mc_blackbox_cfem.py as written (argument parsing, config.mat, the
+    generated-model module written by ``print_code`` and imported back, the
+    split of the record, both problem objects) on an experiment directory
+    made here after mc_data_gen.m; the script itself stops after constructing
+    the first pair of problems (its ``estimate`` is a stub)."""
+    code = MC_RUNNER % {'root': ROOT, 'ref': REF,
+                        'script': os.path.join(REF, 'mc_blackbox_cfem.py')}
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-4000:])
+    assert out.stdout.strip().endswith('ok')
