@@ -6,7 +6,7 @@ spending GPU time: the interior-point driver produces the same iterates with
 oracle and with CUDA callbacks (tests/test_gpu_nlp.py), so which attempt
 solves a seed is the same on both.  Test / analysis infrastructure only.
 
-    python tools/mc_cpu_attempts.py --seeds 28,31,34 --from-attempt 4 \
+    python tests/mc_cpu_attempts.py --seeds 28,31,34 --from-attempt 4 \
         > profiles/r02_mc_unsolved_seeds_cpu.jsonl
 """
 import argparse
@@ -18,7 +18,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))     # tests/ -> repo root
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
